@@ -1,0 +1,41 @@
+# Builds the product library (libvlitefast.so, sm_100a only), the C host
+# executables and the test oracles.  Everything lands in-tree so that it
+# travels to the GPU box with the snapshot.
+NVCC     ?= /usr/local/cuda/bin/nvcc
+# the image exports CC=/opt/gcc/bin/gcc, a wrapper without libgomp
+HOSTCC   := /usr/bin/gcc
+GENCODE  := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := -O3 -std=c++17 $(GENCODE) -lineinfo -Xcompiler -fPIC -Iinclude -Ivlite-fast_b200/csrc
+PKG      := vlite-fast_b200
+CSRC     := $(PKG)/csrc
+HOST     := $(PKG)/host
+LIB      := $(PKG)/libvlitefast.so
+
+all: $(LIB) host oracle build/vf_fft_hosttest
+
+build:
+	mkdir -p build
+
+build/vf_kernels.o: $(CSRC)/vf_kernels.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft12500.cuh $(CSRC)/vf_fft_consts.h | build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+build/vf_api.o: $(CSRC)/vf_api.cu $(CSRC)/vf_kernels.h include/vlitefast.h | build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): build/vf_kernels.o build/vf_api.o
+	$(NVCC) -shared $(GENCODE) -o $@ $^ -ldl
+
+build/vf_fft_hosttest: $(CSRC)/vf_fft_hosttest.cu $(CSRC)/vf_fft12500.cuh | build
+	$(NVCC) -O2 -std=c++17 -I$(CSRC) -o $@ $<
+
+host: $(LIB)
+	@if [ -f $(HOST)/Makefile ]; then $(MAKE) -C $(HOST) HOSTCC=$(HOSTCC); fi
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build $(LIB)
+	$(MAKE) -C oracle clean
+
+.PHONY: all host oracle clean

@@ -1,0 +1,45 @@
+"""Index arithmetic and butterflies of the kernel's 12500-point two-for-one FFT
+(csrc/vf_fft12500.cuh), executed on the CPU by build/vf_fft_hosttest: the same
+__host__ __device__ functions the kernel calls, one loop per barrier interval."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, make_input
+
+EXE = os.path.join(ROOT, "build", "vf_fft_hosttest")
+
+
+def run(b0, b1, mask=0):
+    r = subprocess.run([EXE, "%x" % mask], input=b0.tobytes() + b1.tobytes(), stdout=subprocess.PIPE, check=True)
+    out = np.frombuffer(r.stdout, np.float32)
+    P = out[: 2 * 4096].reshape(4096, 2)
+    Z = out[2 * 4096:].reshape(12500, 2)
+    return P, Z[:, 0] + 1j * Z[:, 1]
+
+
+def volts(u):
+    x = u.astype(np.float64) / 128 - 1
+    x[u == 0] = 0
+    return x
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="build/vf_fft_hosttest not built")
+@pytest.mark.parametrize("mask", [0, 0x1, 0x1555555, 0x1FFFFFE])
+def test_two_for_one_fft(pkg, mask):
+    b0, b1 = make_input(pkg, 1, seed=21)
+    b0 = b0.copy(); b0[100:105] = 0            # dropped samples unpack to 0.0
+    P, Z = run(b0, b1, mask)
+    x0, x1 = volts(b0), volts(b1)
+    for j in range(25):
+        if (mask >> j) & 1:
+            x0[500 * j:500 * (j + 1)] = 0
+            x1[500 * j:500 * (j + 1)] = 0
+    Zr = np.fft.fft(x0 + 1j * x1)
+    scale = np.sqrt((np.abs(Zr) ** 2).mean()) + 1e-30
+    assert np.abs(Z - Zr).max() / scale < 3e-6
+    for pol, x in enumerate((x0, x1)):
+        Pr = np.abs(np.fft.rfft(x)[2155:2155 + 4096]) ** 2
+        assert np.abs(P[:, pol] - Pr).max() / (Pr.mean() + 1e-30) < 1e-5

@@ -1,0 +1,212 @@
+"""-m gpu: libvlitefast (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star): RFI masks and weights
+bit-exact; float spectra / filterbank powers within 1e-5 relative (norm-wise:
+max |diff| / mean power); digitised samples bit-exact
+except rounding-boundary samples, <= 1 LSB in < 1e-4 of samples."""
+import numpy as np
+import pytest
+
+from conftest import make_input, byte_diff, RFI
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5          # north_star tolerance for float spectra / powers
+BYTE_FRAC = 1e-4    # north_star allowance for rounding-boundary samples
+
+
+def check_bytes(a, b, nbit, what):
+    worst, frac = byte_diff(a, b, nbit)
+    nsamp = a.size * (8 // nbit)
+    assert worst <= 1, "%s: code differs by %d" % (what, worst)
+    # at small sizes 1e-4 of the samples is a handful: allow 3 boundary samples
+    assert frac < BYTE_FRAC or frac * nsamp <= 3, "%s: %.3g of samples differ" % (what, frac)
+
+
+def run_both(pkg, orc, T, nbit, npol, mode, seed=1, nseg=1, **gen):
+    p = pkg.Pipeline(ffts_per_seg=T, nbit=nbit, npol=npol, rfi_mode=mode, keep_stats=1, keep_power=1, do_histo=1)
+    o = orc.OracleChain(T, nbit, npol, mode)
+    res = []
+    for s in range(nseg):
+        p0, p1 = make_input(pkg, T, seed=seed, sample0=s * T * 12500, **gen)
+        res.append((p.process_segment(p0, p1), o.process_segment(p0, p1)))
+    return p, o, res
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("nbit,npol", [(2, 1), (8, 1), (4, 2), (8, 2)])
+def test_segment_matches_oracle(pkg, orc, mode, nbit, npol):
+    T = 32
+    p, o, res = run_both(pkg, orc, T, nbit, npol, mode, seed=10 + mode, **RFI)
+    (main, raw), (omain, oraw) = res[0]
+    if mode:
+        assert np.array_equal(p.get_mask(), o.mask())
+        st = p.get_stats()
+        assert np.count_nonzero(p.get_mask()) > 0
+        for k in ("pow", "kur", "dag", "pow_fb", "kur_fb", "weights"):
+            assert np.array_equal(st[k], o.get(k), equal_nan=True), k
+        np.testing.assert_allclose(st["dag_fb"], o.get("dag_fb"), rtol=1e-6)
+        assert np.array_equal(st["histo"], o.get("histo"))
+    det, odet = p.get_detected_power(0, 0), o.power_trimmed("main")
+    assert np.abs(det - odet).max() / odet.mean() < REL
+    ave, oave = p.get_power_f32(0, 0), o.ave_trimmed("main")
+    assert np.abs(ave - oave).max() < 2e-4          # unit-variance quantity: absolute
+    check_bytes(main, omain, nbit, "main")
+    if mode == 2:
+        check_bytes(raw, oraw, nbit, "raw")
+        assert np.abs(p.get_power_f32(0, 1) - o.ave_trimmed("raw")).max() < 2e-4
+    bp, obp = p.get_bandpass(0, 0), o.get("bp_main").reshape(2, 6251)[:, 2155:2155 + 4096]
+    np.testing.assert_allclose(bp, obp, rtol=2e-5)
+    p.close()
+
+
+def test_bandpass_state_across_segments(pkg, orc):
+    T = 16
+    p, o, res = run_both(pkg, orc, T, 8, 1, 2, seed=4, nseg=4, **RFI)
+    for i, ((main, raw), (omain, oraw)) in enumerate(res):
+        check_bytes(main, omain, 8, "main seg %d" % i)
+        check_bytes(raw, oraw, 8, "raw seg %d" % i)
+    p.close()
+
+
+def test_clean_input(pkg, orc):
+    T = 16
+    p, o, res = run_both(pkg, orc, T, 2, 1, 2, seed=77)
+    (main, raw), (omain, oraw) = res[0]
+    assert np.array_equal(p.get_mask(), o.mask())
+    check_bytes(main, omain, 2, "main")
+    check_bytes(raw, oraw, 2, "raw")
+    p.close()
+
+
+def test_all_dropped_segment(pkg, orc):
+    """every frame dropped (bytes 0): all excised, weight 0, bandpass set to 1"""
+    T = 8
+    z = np.zeros(T * 12500, np.uint8)
+    with pkg.Pipeline(ffts_per_seg=T, nbit=2, npol=1, rfi_mode=1, keep_stats=1) as p:
+        main, _ = p.process_segment(z, z)
+        assert np.all(p.get_mask() == (1 << 25) - 1)
+        assert np.all(p.get_stats()["weights"] == 0)
+        assert np.all(p.get_bandpass() == 1)
+        assert np.all(main == 0b01010101)
+
+
+def test_partially_dropped_frames(pkg, orc):
+    T = 16
+    gen = dict(drop_period=7, drop_len=2, drop_pol_skew=3, **RFI)
+    p, o, res = run_both(pkg, orc, T, 8, 2, 2, seed=8, **gen)
+    (main, raw), (omain, oraw) = res[0]
+    assert np.array_equal(p.get_mask(), o.mask())
+    assert np.array_equal(p.get_stats()["weights"], o.get("weights"))
+    check_bytes(main, omain, 8, "main")
+    check_bytes(raw, oraw, 8, "raw")
+    p.close()
+
+
+def test_batch_equals_single(pkg):
+    T, n = 16, 3
+    ins = [make_input(pkg, T, seed=30, antenna=a, **RFI) for a in range(n)]
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, n_antennas=n) as pb:
+        mains, raws = pb.process_batch([i[0] for i in ins], [i[1] for i in ins])
+    for a in range(n):
+        with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2) as p1:
+            m, r = p1.process_segment(*ins[a])
+        assert np.array_equal(m, mains[a]) and np.array_equal(r, raws[a])
+    assert not np.array_equal(mains[0], mains[1])
+
+
+def test_vdif_input_equals_planar(pkg):
+    T = 16
+    nfr = T * 12500 // 5000
+    g = pkg.GenParams.default(seed=12, **RFI)
+    first = 400
+    frames = pkg.gen_vdif_second(g, 0, 1234, first, nfr)
+    s0 = (1234 * 25600 + first) * 5000
+    p0 = pkg.gen_samples(g, 0, 0, s0, T * 12500)
+    p1 = pkg.gen_samples(g, 0, 1, s0, T * 12500)
+    # shuffle frame order: depacketising goes by header, not by position
+    fr = frames.reshape(-1, 5032)
+    perm = np.random.default_rng(0).permutation(fr.shape[0])
+    shuffled = np.ascontiguousarray(fr[perm]).reshape(-1)
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2) as p:
+        m, r = p.process_segment(p0, p1)
+        p.reset_bandpass()
+        mv, rv = p.process_vdif(shuffled, first)
+        assert np.array_equal(m, mv) and np.array_equal(r, rv)
+        p.reset_bandpass()
+        with pytest.raises(pkg.VfError) as e:
+            p.process_vdif(shuffled, first + 1)          # one frame pair falls outside
+        assert e.value.code == 23
+
+
+def test_async_double_buffer_equals_sync(pkg):
+    T, nseg = 16, 6
+    segs = [make_input(pkg, T, seed=40, sample0=s * T * 12500, **RFI) for s in range(nseg)]
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=1) as p:
+        want = [p.process_segment(*s)[0] for s in segs]
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=1) as p:
+        outs = [np.empty(p.out_bytes, np.uint8) for _ in range(nseg)]
+        for s in range(nseg):
+            if s >= 2:
+                p.wait(s & 1)
+            p.submit_async(s & 1, [segs[s][0]], [segs[s][1]], [outs[s]])
+        p.wait(0); p.wait(1)
+        with pytest.raises(pkg.VfError):
+            p.wait(0)
+    for s in range(nseg):
+        assert np.array_equal(outs[s], want[s]), s
+
+
+def test_device_resident_equals_host(pkg):
+    import torch
+    T, nseg, n = 16, 3, 2
+    data = np.empty((nseg, n, 2, T * 12500), np.uint8)
+    for s in range(nseg):
+        for a in range(n):
+            data[s, a, 0], data[s, a, 1] = make_input(pkg, T, seed=50, antenna=a, sample0=s * T * 12500, **RFI)
+    with pkg.Pipeline(ffts_per_seg=T, nbit=2, rfi_mode=2, n_antennas=n) as p:
+        want = [p.process_batch([data[s, a, 0] for a in range(n)], [data[s, a, 1] for a in range(n)]) for s in range(nseg)]
+    with pkg.Pipeline(ffts_per_seg=T, nbit=2, rfi_mode=2, n_antennas=n) as p:
+        d_in = torch.from_numpy(data).cuda()
+        d_main = torch.zeros((nseg, n, p.out_bytes), dtype=torch.uint8, device="cuda")
+        d_raw = torch.zeros_like(d_main)
+        torch.cuda.synchronize()
+        p.process_device(n, nseg, d_in.data_ptr(), d_main.data_ptr(), d_raw.data_ptr())
+        p.sync()
+        total, k1, k2 = p.last_elapsed_ms()
+        assert total > 0 and k1 > 0 and k2 > 0
+        m, r = d_main.cpu().numpy(), d_raw.cpu().numpy()
+    for s in range(nseg):
+        for a in range(n):
+            assert np.array_equal(m[s, a], want[s][0][a]) and np.array_equal(r[s, a], want[s][1][a])
+
+
+def test_k1_thread_variants_agree(pkg):
+    T = 16
+    p0, p1 = make_input(pkg, T, seed=60, **RFI)
+    outs = []
+    for nt in (320, 640):
+        with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, k1_threads=nt) as p:
+            outs.append(p.process_segment(p0, p1))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_coadd_single_process(pkg, orc):
+    """co-add of 3 antennas on one GPU = digitised (sum of the oracle's tiles / sqrt 3)"""
+    T, n = 16, 3
+    ins = [make_input(pkg, T, seed=70, antenna=a, **RFI) for a in range(n)]
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=1, n_antennas=n, keep_power=1) as p:
+        p.process_batch([i[0] for i in ins], [i[1] for i in ins])
+        p.coadd_init()
+        fb, sm = p.coadd_segment(0, n)
+    tiles = []
+    for a in range(n):
+        o = orc.OracleChain(T, 8, 1, 1)
+        o.process_segment(*ins[a])
+        tiles.append(o.ave_trimmed("main"))
+    osum = tiles[0] + tiles[1] + tiles[2]
+    assert np.abs(sm - osum).max() < 5e-4
+    full = np.zeros((1, T // 8, 6251), np.float32)
+    full[:, :, 2155:2155 + 4096] = osum * np.float32(1 / np.sqrt(3.0))
+    want = np.empty(fb.size, np.uint8)
+    orc.liba().orc_digitise(full.ctypes.data, want.ctypes.data, T // 8, 1, 8)
+    check_bytes(fb, want, 8, "coadd")

@@ -1,0 +1,831 @@
+/*
+ * libvlitefast host side: the C ABI of include/vlitefast.h over the sm_100a
+ * kernels of vf_kernels.cu.  It replaces the allocation block and the
+ * per-segment loop body of the reference's main()
+ * (src/process_baseband.cu:472-475, 578-709, 1108-1375).  No CPU fallback:
+ * every entry point that computes needs a CUDA device and fails otherwise.
+ *
+ * Streams.  The handle owns one control stream and two "slots".  A slot is a
+ * stream plus one set of device buffers (samples, power tiles, weights,
+ * packed output).  Consecutive segments alternate between the slots so that
+ * the channeliser (K1) of segment n+1 overlaps the normaliser (K2) and the
+ * copies of segment n.  The only cross-segment dependency of the chain is the
+ * running bandpass (src/pb_kernels.cu:406-428, state :700-709): K2 launches
+ * are chained by an event so that they run in segment order.
+ */
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <dlfcn.h>
+#include <vector>
+#include <cuda_runtime.h>
+#include "vlitefast.h"
+#include "vf_kernels.h"
+
+#define VF_MAX_TIMED_SEG 256
+
+struct vf_slot {
+  cudaStream_t st;
+  uint8_t *d_in;              /* [n_ant][2][T*12500] */
+  uint8_t *d_frames;          /* raw VDIF staging, lazily allocated */
+  size_t frames_cap;
+  float2 *P_raw, *P_kur;      /* [n_ant][T][4096] */
+  float *w;                   /* [n_ant][T] */
+  uint32_t *mask;             /* [n_ant][T] */
+  uint8_t *d_out_main, *d_out_raw;   /* [n_ant][out_bytes] */
+  cudaEvent_t ev_k2, ev_done;
+  int pending;                /* vf_submit_async issued, vf_wait not yet called */
+};
+
+/* minimal NCCL surface, resolved with dlopen at vf_coadd_init */
+typedef struct { char internal[128]; } vf_nccl_id;
+typedef void *vf_nccl_comm;
+struct vf_nccl_api {
+  void *lib;
+  int (*GetUniqueId) (vf_nccl_id *);
+  int (*CommInitRank) (vf_nccl_comm *, int, vf_nccl_id, int);
+  int (*AllReduce) (const void *, void *, size_t, int, int, vf_nccl_comm, cudaStream_t);
+  int (*Reduce) (const void *, void *, size_t, int, int, int, vf_nccl_comm, cudaStream_t);
+  int (*CommDestroy) (vf_nccl_comm);
+  const char *(*GetErrorString) (int);
+};
+static vf_nccl_api g_nccl;
+
+struct vf_handle {
+  vf_config cfg;
+  int T, ntime, n_ant, nsm;
+  size_t nsamp;               /* per pol per segment */
+  size_t out_bytes;           /* per antenna per stream per segment */
+  size_t tile_elems;          /* T*4096 per antenna */
+  cudaStream_t ctl;
+  vf_slot slot[2];
+  int next_slot;              /* slot of the next synchronous segment */
+  int last_slot;              /* slot that holds the last processed segment */
+  cudaEvent_t ev_k2_last;     /* completion of the most recent K2 */
+  int have_k2_last;
+  float2 *bp_raw, *bp_kur;    /* [n_ant][4096] (pol0, pol1) */
+  float2 *tw;                 /* tw1 | tw5 | tw500 */
+  float *wtab;                /* [26] */
+  float *pw, *kur, *dag, *pw_fb, *kur_fb, *dag_fb;
+  unsigned int *histo;
+  float *ave_main, *ave_raw;  /* [n_ant][npol][T/8][4096] */
+  float *frb_delays;
+  int frb_nfft_since; float frb_width, frb_amp; float frb_dm;
+  unsigned int *d_bad, *h_bad;
+  double dagc[5], dagc_fb[5];
+  /* timing */
+  cudaEvent_t ev_t0, ev_t1;
+  cudaEvent_t ev_ka[VF_MAX_TIMED_SEG], ev_kb[VF_MAX_TIMED_SEG], ev_kc[VF_MAX_TIMED_SEG];
+  int n_timed, timed_valid;
+  /* co-add */
+  vf_nccl_comm comm; int nranks, rank;
+  float *coadd_sum; uint8_t *coadd_out;
+  char err[512];
+};
+
+static int vf_fail (vf_handle *h, int code, const char *fmt, ...)
+{
+  if (h) {
+    va_list ap;
+    va_start (ap, fmt);
+    vsnprintf (h->err, sizeof (h->err), fmt, ap);
+    va_end (ap);
+  }
+  return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return vf_fail (h, e_ == cudaErrorMemoryAllocation ? VF_ERR_NOMEM : VF_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString (e_), __FILE__, __LINE__); } while (0)
+
+extern "C" {
+
+const char *vf_strerror (int code)
+{
+  switch (code) {
+    case VF_OK: return "ok";
+    case VF_ERR_ARG: return "bad argument or unsupported configuration";
+    case VF_ERR_CUDA: return "CUDA runtime error";
+    case VF_ERR_NOMEM: return "out of memory";
+    case VF_ERR_STATE: return "call out of sequence";
+    case VF_ERR_VDIF: return "VDIF frames outside the segment or malformed";
+    case VF_ERR_NCCL: return "NCCL error";
+    case VF_ERR_NODEV: return "no usable CUDA device";
+    default: return "unknown error";
+  }
+}
+
+const char *vf_last_error (const vf_handle *h) { return h ? h->err : "null handle"; }
+
+int vf_config_default (vf_config *c)
+{
+  if (!c) return VF_ERR_ARG;
+  memset (c, 0, sizeof (*c));
+  c->abi_version = VF_ABI_VERSION;
+  c->nfft = VF_NFFT;             /* src/process_baseband.h:20 */
+  c->nscrunch = VF_NSCRUNCH;     /* :24 */
+  c->ffts_per_seg = 1024;        /* :28 */
+  c->nkurto = VF_NKURTO;         /* :35 */
+  c->chanmin = VF_CHANMIN;       /* :53 */
+  c->chanmax = VF_CHANMAX;       /* :54 */
+  c->nbit = 2;                   /* src/process_baseband.cu:34 */
+  c->npol = 1;                   /* :349 */
+  c->rfi_mode = 2;               /* :351 */
+  c->n_antennas = 1;
+  return VF_OK;
+}
+
+/* Anscombe-Glynn constants with the reference's mixed float/double macro
+ * expressions, src/pb_kernels.cu:3-20: the sample count is a float, every
+ * literal a double.  out = {mu1, A, Z1, Z2, Z3}. */
+static void vf_dag_constants (int nsamp, double out[5])
+{
+  const float n = (float) nsamp;
+  const double mu1 = -6. / (n + 1);
+  const double mu2 = (24. * n * (n - 2) * (n - 3)) / ((n + 1) * (n + 1) * (n + 3) * (n + 5));
+  const double g1 = 6. * (n * n - 5 * n + 2) / ((n + 7) * (n + 9))
+                    * sqrt ((6. * (n + 3) * (n + 5)) / (n * (n - 2) * (n - 3)));
+  const double A = 6. + (8. / g1) * (2. / g1 + sqrt (1. + 4. / (g1 * g1)));
+  out[0] = mu1; out[1] = A; out[2] = sqrt (4.5 * A); out[3] = 1 - 2. / (9 * A);
+  out[4] = sqrt (2. / (mu2 * (A - 4)));
+}
+
+static int vf_alloc_slot (vf_handle *h, vf_slot *s)
+{
+  const size_t na = (size_t) h->n_ant;
+  const int mode = h->cfg.rfi_mode;
+  CK (cudaStreamCreateWithFlags (&s->st, cudaStreamNonBlocking));
+  CK (cudaMalloc ((void **) &s->d_in, na * 2 * h->nsamp));
+  if (mode != 1) CK (cudaMalloc ((void **) &s->P_raw, na * h->tile_elems * sizeof (float2)));
+  if (mode != 0) CK (cudaMalloc ((void **) &s->P_kur, na * h->tile_elems * sizeof (float2)));
+  CK (cudaMalloc ((void **) &s->w, na * h->T * sizeof (float)));
+  CK (cudaMalloc ((void **) &s->mask, na * h->T * sizeof (uint32_t)));
+  CK (cudaMemset (s->w, 0, na * h->T * sizeof (float)));
+  CK (cudaMemset (s->mask, 0, na * h->T * sizeof (uint32_t)));
+  CK (cudaMalloc ((void **) &s->d_out_main, na * h->out_bytes));
+  if (mode == 2) CK (cudaMalloc ((void **) &s->d_out_raw, na * h->out_bytes));
+  CK (cudaEventCreateWithFlags (&s->ev_k2, cudaEventDisableTiming));
+  CK (cudaEventCreateWithFlags (&s->ev_done, cudaEventDisableTiming));
+  return VF_OK;
+}
+
+int vf_destroy (vf_handle *h)
+{
+  if (!h) return VF_OK;
+  cudaSetDevice (h->cfg.gpu_id);
+  cudaDeviceSynchronize ();
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy (h->comm);
+  for (int i = 0; i < 2; ++i) {
+    vf_slot *s = &h->slot[i];
+    cudaFree (s->d_in); cudaFree (s->d_frames); cudaFree (s->P_raw); cudaFree (s->P_kur);
+    cudaFree (s->w); cudaFree (s->mask); cudaFree (s->d_out_main); cudaFree (s->d_out_raw);
+    if (s->ev_k2) cudaEventDestroy (s->ev_k2);
+    if (s->ev_done) cudaEventDestroy (s->ev_done);
+    if (s->st) cudaStreamDestroy (s->st);
+  }
+  cudaFree (h->bp_raw); cudaFree (h->bp_kur); cudaFree (h->tw); cudaFree (h->wtab);
+  cudaFree (h->pw); cudaFree (h->pw_fb); cudaFree (h->histo); cudaFree (h->ave_main); cudaFree (h->ave_raw);
+  cudaFree (h->frb_delays); cudaFree (h->d_bad); cudaFree (h->coadd_sum); cudaFree (h->coadd_out);
+  if (h->h_bad) cudaFreeHost (h->h_bad);
+  if (h->ev_t0) cudaEventDestroy (h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy (h->ev_t1);
+  if (h->ev_k2_last) cudaEventDestroy (h->ev_k2_last);
+  for (int i = 0; i < VF_MAX_TIMED_SEG; ++i) {
+    if (h->ev_ka[i]) cudaEventDestroy (h->ev_ka[i]);
+    if (h->ev_kb[i]) cudaEventDestroy (h->ev_kb[i]);
+    if (h->ev_kc[i]) cudaEventDestroy (h->ev_kc[i]);
+  }
+  if (h->ctl) cudaStreamDestroy (h->ctl);
+  free (h);
+  return VF_OK;
+}
+
+int vf_create (const vf_config *cfg, vf_handle **out)
+{
+  if (!cfg || !out) return VF_ERR_ARG;
+  *out = NULL;
+  if (cfg->abi_version != VF_ABI_VERSION) return VF_ERR_ARG;
+  /* geometry the kernels are written for (reference defaults,
+   * src/process_baseband.h:16-55); sanity checks of :535-538, :667-672 */
+  if (cfg->nfft != VF_NFFT || cfg->nscrunch != VF_NSCRUNCH || cfg->nkurto != VF_NKURTO) return VF_ERR_ARG;
+  if (cfg->chanmin != VF_CHANMIN || cfg->chanmax != VF_CHANMAX) return VF_ERR_ARG;
+  if (cfg->ffts_per_seg <= 0 || cfg->ffts_per_seg % VF_NSCRUNCH) return VF_ERR_ARG;
+  if (!(cfg->nbit == 2 || cfg->nbit == 4 || cfg->nbit == 8)) return VF_ERR_ARG;
+  if (!(cfg->npol == 1 || cfg->npol == 2)) return VF_ERR_ARG;
+  if (cfg->rfi_mode < 0 || cfg->rfi_mode > 2) return VF_ERR_ARG;
+  if (cfg->n_antennas < 1 || cfg->n_antennas > 4096) return VF_ERR_ARG;
+  if (!(cfg->k1_threads == 0 || cfg->k1_threads == 320 || cfg->k1_threads == 640)) return VF_ERR_ARG;
+
+  int ndev = 0;
+  if (cudaGetDeviceCount (&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError (); return VF_ERR_NODEV; }
+  if (cfg->gpu_id < 0 || cfg->gpu_id >= ndev) return VF_ERR_NODEV;
+
+  vf_handle *h = (vf_handle *) calloc (1, sizeof (*h));
+  if (!h) return VF_ERR_NOMEM;
+  h->cfg = *cfg;
+  *out = h;    /* handed back even on failure so that vf_last_error works; caller destroys */
+  h->T = cfg->ffts_per_seg;
+  h->ntime = h->T / VF_NSCRUNCH;
+  h->n_ant = cfg->n_antennas;
+  h->nsamp = (size_t) h->T * VF_NFFT;
+  h->out_bytes = (size_t) h->ntime * cfg->npol * VF_NCHANOUT * cfg->nbit / 8;
+  h->tile_elems = (size_t) h->T * VF_NCHANOUT;
+  h->frb_nfft_since = -1;
+
+  CK (cudaSetDevice (cfg->gpu_id));
+  cudaDeviceProp prop;
+  CK (cudaGetDeviceProperties (&prop, cfg->gpu_id));
+  if (prop.major < 10)
+    return vf_fail (h, VF_ERR_NODEV, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    cfg->gpu_id, prop.major, prop.minor);
+  h->nsm = prop.multiProcessorCount;
+  CK (vf_k1_configure ());
+  CK (cudaStreamCreateWithFlags (&h->ctl, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    int rc = vf_alloc_slot (h, &h->slot[i]);
+    if (rc) return rc;
+  }
+  const size_t na = (size_t) h->n_ant;
+  CK (cudaMalloc ((void **) &h->bp_raw, na * VF_NCHANOUT * sizeof (float2)));
+  CK (cudaMemset (h->bp_raw, 0, na * VF_NCHANOUT * sizeof (float2)));
+  if (cfg->rfi_mode == 2) {
+    CK (cudaMalloc ((void **) &h->bp_kur, na * VF_NCHANOUT * sizeof (float2)));
+    CK (cudaMemset (h->bp_kur, 0, na * VF_NCHANOUT * sizeof (float2)));
+  }
+
+  /* FFT twiddles in double, rounded once to float */
+  {
+    std::vector<float2> tw (1500);
+    for (int p = 0; p < 500; ++p) {
+      const double a1 = -2.0 * M_PI * p / 12500.0, a5 = -2.0 * M_PI * 5 * p / 12500.0, a500 = -2.0 * M_PI * p / 500.0;
+      tw[p] = make_float2 ((float) cos (a1), (float) sin (a1));
+      tw[500 + p] = make_float2 ((float) cos (a5), (float) sin (a5));
+      tw[1000 + p] = make_float2 ((float) cos (a500), (float) sin (a500));
+    }
+    CK (cudaMalloc ((void **) &h->tw, 1500 * sizeof (float2)));
+    CK (cudaMemcpy (h->tw, tw.data (), 1500 * sizeof (float2), cudaMemcpyHostToDevice));
+  }
+  /* weight of an FFT block with k kept sub-blocks: k sequential float adds of
+   * float(NKURTO)/NFFT (atomicAdd, src/pb_kernels.cu:292) */
+  {
+    float wt[VF_NSUB + 1];
+    const float inc = (float) VF_NKURTO / VF_NFFT;
+    float acc = 0.f;
+    wt[0] = 0.f;
+    for (int k = 1; k <= VF_NSUB; ++k) { acc += inc; wt[k] = acc; }
+    CK (cudaMalloc ((void **) &h->wtab, sizeof (wt)));
+    CK (cudaMemcpy (h->wtab, wt, sizeof (wt), cudaMemcpyHostToDevice));
+  }
+  vf_dag_constants (VF_NKURTO, h->dagc);
+  vf_dag_constants (VF_NFFT, h->dagc_fb);
+
+  if (cfg->keep_stats && cfg->rfi_mode) {
+    const size_t nblk = (size_t) h->T * VF_NSUB;
+    CK (cudaMalloc ((void **) &h->pw, na * 6 * nblk * sizeof (float)));
+    h->kur = h->pw + na * 2 * nblk;
+    h->dag = h->pw + na * 4 * nblk;
+    CK (cudaMalloc ((void **) &h->pw_fb, na * 6 * h->T * sizeof (float)));
+    h->kur_fb = h->pw_fb + na * 2 * h->T;
+    h->dag_fb = h->pw_fb + na * 4 * h->T;
+  }
+  if (cfg->do_histo) CK (cudaMalloc ((void **) &h->histo, na * 512 * sizeof (unsigned int)));
+  if (cfg->keep_power) {
+    const size_t n = na * cfg->npol * h->ntime * VF_NCHANOUT;
+    CK (cudaMalloc ((void **) &h->ave_main, n * sizeof (float)));
+    CK (cudaMemset (h->ave_main, 0, n * sizeof (float)));
+    if (cfg->rfi_mode == 2) {
+      CK (cudaMalloc ((void **) &h->ave_raw, n * sizeof (float)));
+      CK (cudaMemset (h->ave_raw, 0, n * sizeof (float)));
+    }
+  }
+  CK (cudaMalloc ((void **) &h->d_bad, sizeof (unsigned int)));
+  CK (cudaMallocHost ((void **) &h->h_bad, sizeof (unsigned int)));
+  CK (cudaEventCreate (&h->ev_t0));
+  CK (cudaEventCreate (&h->ev_t1));
+  CK (cudaEventCreateWithFlags (&h->ev_k2_last, cudaEventDisableTiming));
+  CK (cudaDeviceSynchronize ());
+  return VF_OK;
+}
+
+size_t vf_segment_out_bytes (const vf_handle *h) { return h ? h->out_bytes : 0; }
+size_t vf_segment_in_samples (const vf_handle *h) { return h ? h->nsamp : 0; }
+
+int vf_host_alloc (void **p, size_t bytes)
+{
+  if (!p) return VF_ERR_ARG;
+  cudaError_t e = cudaMallocHost (p, bytes);
+  return e == cudaSuccess ? VF_OK : (e == cudaErrorMemoryAllocation ? VF_ERR_NOMEM : VF_ERR_CUDA);
+}
+
+int vf_host_free (void *p) { return cudaFreeHost (p) == cudaSuccess ? VF_OK : VF_ERR_CUDA; }
+
+/* ---- the launch sequence of one segment on one slot ---------------------- *
+ * d_in: [n_ant][2][T*12500] on the device.  Outputs to d_main / d_raw
+ * ([n_ant][out_bytes]).  timed >= 0: record the K1/K2 events of that index. */
+static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_t *d_in,
+                               uint8_t *d_main, uint8_t *d_raw, int timed)
+{
+  const vf_config &c = h->cfg;
+  vf_k1_params k1;
+  memset (&k1, 0, sizeof (k1));
+  k1.in = d_in;
+  k1.pol_stride = h->nsamp;
+  k1.ant_stride = 2 * h->nsamp;
+  k1.T = h->T; k1.n_ant = n_ant; k1.rfi_mode = c.rfi_mode;
+  k1.P_raw = s->P_raw; k1.P_kur = s->P_kur;
+  k1.w = s->w; k1.mask = s->mask;
+  k1.pw = h->pw; k1.kur = h->kur; k1.dag = h->dag;
+  k1.pw_fb = h->pw_fb; k1.kur_fb = h->kur_fb; k1.dag_fb = h->dag_fb;
+  k1.histo = h->histo;
+  k1.tb.tw1 = h->tw; k1.tb.tw5 = h->tw + 500; k1.tb.tw500 = h->tw + 1000;
+  memcpy (k1.dagc, h->dagc, sizeof (k1.dagc));
+  memcpy (k1.dagc_fb, h->dagc_fb, sizeof (k1.dagc_fb));
+  k1.wtab = h->wtab;
+  if (c.inject_frb && h->frb_nfft_since >= 0 && h->frb_delays) {
+    k1.frb_delays = h->frb_delays;
+    k1.nfft_since_frb = h->frb_nfft_since;
+    k1.frb_width = h->frb_width; k1.frb_amp = h->frb_amp;
+  }
+  if (h->histo) CK (cudaMemsetAsync (h->histo, 0, (size_t) n_ant * 512 * sizeof (unsigned int), s->st));
+  const int n_items = n_ant * h->T;
+  const int grid = n_items < h->nsm ? n_items : h->nsm;
+  const int threads = c.k1_threads ? c.k1_threads : 640;
+  if (timed >= 0) CK (cudaEventRecord (h->ev_ka[timed], s->st));
+  CK (vf_launch_k1 (k1, grid, threads, s->st));
+  if (timed >= 0) CK (cudaEventRecord (h->ev_kb[timed], s->st));
+
+  /* the bandpass makes K2 launches sequential in segment order */
+  if (h->have_k2_last) CK (cudaStreamWaitEvent (s->st, h->ev_k2_last, 0));
+  vf_k2_params k2;
+  memset (&k2, 0, sizeof (k2));
+  k2.P_raw = s->P_raw; k2.P_kur = s->P_kur; k2.w = s->w; k2.mask = s->mask;
+  k2.bp_raw = h->bp_raw; k2.bp_kur = (c.rfi_mode == 2) ? h->bp_kur : h->bp_raw;
+  k2.T = h->T; k2.n_ant = n_ant; k2.rfi_mode = c.rfi_mode; k2.npol = c.npol; k2.nbit = c.nbit;
+  /* bp_scale = float(tsamp/tsmooth), src/process_baseband.cu:737-741 */
+  k2.bp_scale = (float) (((double) VF_NFFT / 128000000 * VF_NSCRUNCH) / 1.0);
+  k2.out_main = d_main; k2.out_raw = d_raw; k2.out_stride = h->out_bytes;
+  k2.ave_main = h->ave_main; k2.ave_raw = h->ave_raw;
+  CK (vf_launch_k2 (k2, s->st));
+  if (timed >= 0) CK (cudaEventRecord (h->ev_kc[timed], s->st));
+  CK (cudaEventRecord (h->ev_k2_last, s->st));
+  h->have_k2_last = 1;
+  return VF_OK;
+}
+
+static int vf_timing_begin (vf_handle *h, int n_timed)
+{
+  if (n_timed > VF_MAX_TIMED_SEG) n_timed = 0;   /* too many to time per kernel: total only */
+  for (int i = 0; i < n_timed; ++i)
+    if (!h->ev_ka[i]) {
+      CK (cudaEventCreate (&h->ev_ka[i]));
+      CK (cudaEventCreate (&h->ev_kb[i]));
+      CK (cudaEventCreate (&h->ev_kc[i]));
+    }
+  h->n_timed = n_timed;
+  h->timed_valid = 0;
+  /* fork: both slot streams start after ev_t0 on the control stream */
+  CK (cudaEventRecord (h->ev_t0, h->ctl));
+  CK (cudaStreamWaitEvent (h->slot[0].st, h->ev_t0, 0));
+  CK (cudaStreamWaitEvent (h->slot[1].st, h->ev_t0, 0));
+  return VF_OK;
+}
+
+static int vf_timing_end (vf_handle *h)
+{
+  /* join */
+  for (int i = 0; i < 2; ++i) {
+    CK (cudaEventRecord (h->slot[i].ev_done, h->slot[i].st));
+    CK (cudaStreamWaitEvent (h->ctl, h->slot[i].ev_done, 0));
+  }
+  CK (cudaEventRecord (h->ev_t1, h->ctl));
+  h->timed_valid = 1;
+  return VF_OK;
+}
+
+static int vf_check_batch (vf_handle *h, int n_ant, size_t nsamp_per_pol)
+{
+  if (!h) return VF_ERR_ARG;
+  if (n_ant < 1 || n_ant > h->n_ant) return vf_fail (h, VF_ERR_ARG, "n_ant %d outside 1..%d", n_ant, h->n_ant);
+  if (nsamp_per_pol != h->nsamp)
+    return vf_fail (h, VF_ERR_ARG, "nsamp_per_pol %zu != ffts_per_seg*12500 = %zu", nsamp_per_pol, h->nsamp);
+  return VF_OK;
+}
+
+int vf_submit_async (vf_handle *h, int slot, int n_ant,
+                     const uint8_t *const *pol0, const uint8_t *const *pol1, size_t nsamp_per_pol,
+                     uint8_t *const *fb_main, uint8_t *const *fb_raw)
+{
+  int rc = vf_check_batch (h, n_ant, nsamp_per_pol);
+  if (rc) return rc;
+  if (slot < 0 || slot > 1 || !pol0 || !pol1 || !fb_main) return vf_fail (h, VF_ERR_ARG, "bad slot or null array");
+  vf_slot *s = &h->slot[slot];
+  if (s->pending) return vf_fail (h, VF_ERR_STATE, "slot %d submitted twice without vf_wait", slot);
+  CK (cudaSetDevice (h->cfg.gpu_id));
+  for (int a = 0; a < n_ant; ++a) {                       /* H2D, src/process_baseband.cu:1117-1122 */
+    if (!pol0[a] || !pol1[a] || !fb_main[a]) return vf_fail (h, VF_ERR_ARG, "null buffer for antenna %d", a);
+    CK (cudaMemcpyAsync (s->d_in + (size_t) a * 2 * h->nsamp, pol0[a], h->nsamp, cudaMemcpyHostToDevice, s->st));
+    CK (cudaMemcpyAsync (s->d_in + ((size_t) a * 2 + 1) * h->nsamp, pol1[a], h->nsamp, cudaMemcpyHostToDevice, s->st));
+  }
+  rc = vf_enqueue_segment (h, s, n_ant, s->d_in, s->d_out_main, s->d_out_raw, -1);
+  if (rc) return rc;
+  for (int a = 0; a < n_ant; ++a) {                       /* D2H, :1370-1375 */
+    CK (cudaMemcpyAsync (fb_main[a], s->d_out_main + (size_t) a * h->out_bytes, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
+    if (h->cfg.rfi_mode == 2 && fb_raw && fb_raw[a])
+      CK (cudaMemcpyAsync (fb_raw[a], s->d_out_raw + (size_t) a * h->out_bytes, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
+  }
+  CK (cudaEventRecord (s->ev_done, s->st));
+  s->pending = 1;
+  h->last_slot = slot;
+  return VF_OK;
+}
+
+int vf_wait (vf_handle *h, int slot)
+{
+  if (!h || slot < 0 || slot > 1) return VF_ERR_ARG;
+  vf_slot *s = &h->slot[slot];
+  if (!s->pending) return vf_fail (h, VF_ERR_STATE, "vf_wait (%d) without vf_submit_async", slot);
+  s->pending = 0;
+  CK (cudaEventSynchronize (s->ev_done));
+  return VF_OK;
+}
+
+int vf_process_batch (vf_handle *h, int n_ant,
+                      const uint8_t *const *pol0, const uint8_t *const *pol1, size_t nsamp_per_pol,
+                      uint8_t *const *fb_main, uint8_t *const *fb_raw)
+{
+  if (!h) return VF_ERR_ARG;
+  const int slot = h->next_slot;
+  if (h->slot[slot].pending) return vf_fail (h, VF_ERR_STATE, "slot %d has an asynchronous segment in flight", slot);
+  int rc = vf_timing_begin (h, 0);
+  if (rc) return rc;
+  rc = vf_submit_async (h, slot, n_ant, pol0, pol1, nsamp_per_pol, fb_main, fb_raw);
+  if (rc) return rc;
+  rc = vf_timing_end (h);
+  if (rc) { h->slot[slot].pending = 0; return rc; }
+  h->next_slot ^= 1;
+  return vf_wait (h, slot);
+}
+
+int vf_process_segment (vf_handle *h, int antenna,
+                        const uint8_t *pol0, const uint8_t *pol1, size_t nsamp_per_pol,
+                        uint8_t *fb_main, uint8_t *fb_raw, size_t *nbytes)
+{
+  if (!h) return VF_ERR_ARG;
+  if (antenna != 0)
+    return vf_fail (h, VF_ERR_ARG, "vf_process_segment drives antenna 0 of the handle; batch the others with vf_process_batch");
+  const uint8_t *p0[1] = { pol0 }, *p1[1] = { pol1 };
+  uint8_t *m[1] = { fb_main }, *r[1] = { fb_raw };
+  int rc = vf_process_batch (h, 1, p0, p1, nsamp_per_pol, m, r);
+  if (rc == VF_OK && nbytes) *nbytes = h->out_bytes;
+  return rc;
+}
+
+int vf_process_vdif (vf_handle *h, int antenna, const void *frames, size_t nframes,
+                     uint32_t first_frame, uint8_t *fb_main, uint8_t *fb_raw, size_t *nbytes)
+{
+  if (!h || !frames || !fb_main) return VF_ERR_ARG;
+  if (antenna != 0) return vf_fail (h, VF_ERR_ARG, "vf_process_vdif drives antenna 0 of the handle");
+  const size_t per_pol = h->nsamp / VF_VD_DAT;            /* frames per pol per segment */
+  if (nframes > 4 * per_pol) return vf_fail (h, VF_ERR_ARG, "%zu frames for a segment of %zu", nframes, 2 * per_pol);
+  const int slot = h->next_slot;
+  vf_slot *s = &h->slot[slot];
+  if (s->pending) return vf_fail (h, VF_ERR_STATE, "slot %d has an asynchronous segment in flight", slot);
+  CK (cudaSetDevice (h->cfg.gpu_id));
+  const size_t bytes = nframes * VF_VD_FRM;
+  if (s->frames_cap < bytes) {
+    cudaFree (s->d_frames); s->d_frames = NULL; s->frames_cap = 0;
+    size_t cap = bytes > 2 * per_pol * VF_VD_FRM ? bytes : 2 * per_pol * VF_VD_FRM;
+    CK (cudaMalloc ((void **) &s->d_frames, cap));
+    s->frames_cap = cap;
+  }
+  int rc = vf_timing_begin (h, 0);
+  if (rc) return rc;
+  CK (cudaMemcpyAsync (s->d_frames, frames, bytes, cudaMemcpyHostToDevice, s->st));
+  /* frames the writer never delivered stay zero, i.e. "dropped" samples
+   * (src/writer.c:362,674-687; byte 0 -> 0.0, src/pb_kernels.cu:28-29) */
+  CK (cudaMemsetAsync (s->d_in, 0, 2 * h->nsamp, s->st));
+  CK (cudaMemsetAsync (h->d_bad, 0, sizeof (unsigned int), s->st));
+  vf_depack_params dp;
+  dp.frames = s->d_frames; dp.nframes = nframes; dp.out = s->d_in; dp.pol_stride = h->nsamp;
+  dp.frame0 = first_frame; dp.nframes_per_pol = (long long) per_pol; dp.bad = h->d_bad;
+  CK (vf_launch_depack (dp, s->st));
+  CK (cudaMemcpyAsync (h->h_bad, h->d_bad, sizeof (unsigned int), cudaMemcpyDeviceToHost, s->st));
+  rc = vf_enqueue_segment (h, s, 1, s->d_in, s->d_out_main, s->d_out_raw, -1);
+  if (rc) return rc;
+  CK (cudaMemcpyAsync (fb_main, s->d_out_main, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
+  if (h->cfg.rfi_mode == 2 && fb_raw)
+    CK (cudaMemcpyAsync (fb_raw, s->d_out_raw, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
+  rc = vf_timing_end (h);
+  if (rc) return rc;
+  CK (cudaStreamSynchronize (h->ctl));
+  h->last_slot = slot;
+  h->next_slot ^= 1;
+  if (nbytes) *nbytes = h->out_bytes;
+  if (*h->h_bad)
+    return vf_fail (h, VF_ERR_VDIF, "%u frame(s) outside the segment starting at frame %u", *h->h_bad, first_frame);
+  return VF_OK;
+}
+
+int vf_process_device (vf_handle *h, int n_ant, int n_seg, const uint8_t *d_in,
+                       uint8_t *d_fb_main, uint8_t *d_fb_raw)
+{
+  if (!h || !d_in || !d_fb_main || n_seg < 1) return VF_ERR_ARG;
+  if (n_ant < 1 || n_ant > h->n_ant) return vf_fail (h, VF_ERR_ARG, "n_ant %d outside 1..%d", n_ant, h->n_ant);
+  if (((uintptr_t) d_in) & 15) return vf_fail (h, VF_ERR_ARG, "d_in must be 16-byte aligned");
+  if (h->cfg.rfi_mode == 2 && !d_fb_raw) return vf_fail (h, VF_ERR_ARG, "rfi_mode 2 needs d_fb_raw");
+  if (h->slot[0].pending || h->slot[1].pending) return vf_fail (h, VF_ERR_STATE, "asynchronous segment in flight");
+  CK (cudaSetDevice (h->cfg.gpu_id));
+  int rc = vf_timing_begin (h, n_seg);
+  if (rc) return rc;
+  const size_t in_seg = (size_t) n_ant * 2 * h->nsamp, out_seg = (size_t) n_ant * h->out_bytes;
+  for (int sg = 0; sg < n_seg; ++sg) {
+    vf_slot *s = &h->slot[h->next_slot];
+    rc = vf_enqueue_segment (h, s, n_ant, d_in + (size_t) sg * in_seg, d_fb_main + (size_t) sg * out_seg,
+                             d_fb_raw ? d_fb_raw + (size_t) sg * out_seg : NULL, sg < h->n_timed ? sg : -1);
+    if (rc) return rc;
+    h->last_slot = h->next_slot;
+    h->next_slot ^= 1;
+  }
+  return vf_timing_end (h);
+}
+
+int vf_sync (vf_handle *h)
+{
+  if (!h) return VF_ERR_ARG;
+  CK (cudaStreamSynchronize (h->ctl));
+  CK (cudaStreamSynchronize (h->slot[0].st));
+  CK (cudaStreamSynchronize (h->slot[1].st));
+  return VF_OK;
+}
+
+int vf_last_elapsed_ms (vf_handle *h, float *total_ms, float *k1_ms, float *k2_ms)
+{
+  if (!h) return VF_ERR_ARG;
+  if (!h->timed_valid) return vf_fail (h, VF_ERR_STATE, "nothing timed yet");
+  CK (cudaEventSynchronize (h->ev_t1));
+  if (total_ms) CK (cudaEventElapsedTime (total_ms, h->ev_t0, h->ev_t1));
+  float a = 0.f, b = 0.f;
+  for (int i = 0; i < h->n_timed; ++i) {
+    float x = 0.f, y = 0.f;
+    CK (cudaEventElapsedTime (&x, h->ev_ka[i], h->ev_kb[i]));
+    CK (cudaEventElapsedTime (&y, h->ev_kb[i], h->ev_kc[i]));
+    a += x; b += y;
+  }
+  /* sums over the segments of the last vf_process_device call; k2 includes
+   * any wait for the previous segment's K2 (bandpass order) */
+  if (k1_ms) *k1_ms = a;
+  if (k2_ms) *k2_ms = b;
+  return VF_OK;
+}
+
+/* ---- inspection ----------------------------------------------------------- */
+static int vf_check_ant (vf_handle *h, int antenna)
+{
+  if (!h) return VF_ERR_ARG;
+  if (antenna < 0 || antenna >= h->n_ant) return vf_fail (h, VF_ERR_ARG, "antenna %d outside 0..%d", antenna, h->n_ant - 1);
+  return VF_OK;
+}
+
+int vf_get_stats (vf_handle *h, int antenna, float *pw, float *kur, float *dag,
+                  float *pw_fb, float *kur_fb, float *dag_fb, float *weights, uint32_t *histo)
+{
+  int rc = vf_check_ant (h, antenna);
+  if (rc) return rc;
+  rc = vf_sync (h);
+  if (rc) return rc;
+  const size_t nblk = (size_t) h->T * VF_NSUB, T = h->T;
+  if (pw || kur || dag || pw_fb || kur_fb || dag_fb) {
+    if (!h->pw) return vf_fail (h, VF_ERR_STATE, "statistics need keep_stats and rfi_mode != 0");
+    if (pw) CK (cudaMemcpy (pw, h->pw + (size_t) antenna * 2 * nblk, 2 * nblk * 4, cudaMemcpyDeviceToHost));
+    if (kur) CK (cudaMemcpy (kur, h->kur + (size_t) antenna * 2 * nblk, 2 * nblk * 4, cudaMemcpyDeviceToHost));
+    if (dag) CK (cudaMemcpy (dag, h->dag + (size_t) antenna * 2 * nblk, 2 * nblk * 4, cudaMemcpyDeviceToHost));
+    if (pw_fb) CK (cudaMemcpy (pw_fb, h->pw_fb + (size_t) antenna * 2 * T, 2 * T * 4, cudaMemcpyDeviceToHost));
+    if (kur_fb) CK (cudaMemcpy (kur_fb, h->kur_fb + (size_t) antenna * 2 * T, 2 * T * 4, cudaMemcpyDeviceToHost));
+    if (dag_fb) CK (cudaMemcpy (dag_fb, h->dag_fb + (size_t) antenna * 2 * T, 2 * T * 4, cudaMemcpyDeviceToHost));
+  }
+  if (weights) {
+    if (!h->cfg.rfi_mode) return vf_fail (h, VF_ERR_STATE, "weights need rfi_mode != 0");
+    /* both pols always carry the same weight (src/pb_kernels.cu:132) */
+    CK (cudaMemcpy (weights, h->slot[h->last_slot].w + (size_t) antenna * T, T * 4, cudaMemcpyDeviceToHost));
+    memcpy (weights + T, weights, T * 4);
+  }
+  if (histo) {
+    if (!h->histo) return vf_fail (h, VF_ERR_STATE, "histogram needs do_histo");
+    CK (cudaMemcpy (histo, h->histo + (size_t) antenna * 512, 512 * 4, cudaMemcpyDeviceToHost));
+  }
+  return VF_OK;
+}
+
+int vf_get_mask (vf_handle *h, int antenna, uint32_t *mask)
+{
+  int rc = vf_check_ant (h, antenna);
+  if (rc) return rc;
+  if (!mask) return VF_ERR_ARG;
+  rc = vf_sync (h);
+  if (rc) return rc;
+  CK (cudaMemcpy (mask, h->slot[h->last_slot].mask + (size_t) antenna * h->T, (size_t) h->T * 4, cudaMemcpyDeviceToHost));
+  return VF_OK;
+}
+
+int vf_get_power_f32 (vf_handle *h, int antenna, int which, float *out)
+{
+  int rc = vf_check_ant (h, antenna);
+  if (rc) return rc;
+  if (!out || which < 0 || which > 1) return VF_ERR_ARG;
+  const float *src = which ? h->ave_raw : h->ave_main;
+  if (!src) return vf_fail (h, VF_ERR_STATE, "needs keep_power (and rfi_mode 2 for which = 1)");
+  rc = vf_sync (h);
+  if (rc) return rc;
+  const size_t n = (size_t) h->cfg.npol * h->ntime * VF_NCHANOUT;
+  CK (cudaMemcpy (out, src + (size_t) antenna * n, n * 4, cudaMemcpyDeviceToHost));
+  return VF_OK;
+}
+
+int vf_get_detected_power (vf_handle *h, int antenna, int which, float *out)
+{
+  int rc = vf_check_ant (h, antenna);
+  if (rc) return rc;
+  if (!out || which < 0 || which > 1) return VF_ERR_ARG;
+  const int mode = h->cfg.rfi_mode;
+  if (which == 1 && mode != 2) return vf_fail (h, VF_ERR_STATE, "raw stream beside the main one needs rfi_mode 2");
+  rc = vf_sync (h);
+  if (rc) return rc;
+  vf_slot *s = &h->slot[h->last_slot];
+  const size_t n = h->tile_elems, off = (size_t) antenna * n;
+  const bool want_kur = (which == 0 && mode != 0);
+  if (!want_kur) {
+    CK (cudaMemcpy (out, s->P_raw + off, n * sizeof (float2), cudaMemcpyDeviceToHost));
+    return VF_OK;
+  }
+  CK (cudaMemcpy (out, s->P_kur + off, n * sizeof (float2), cudaMemcpyDeviceToHost));
+  if (mode == 2) {
+    /* time steps with an empty mask were not re-transformed: identical to raw */
+    std::vector<uint32_t> mk (h->T);
+    std::vector<float> row (2 * VF_NCHANOUT);
+    CK (cudaMemcpy (mk.data (), s->mask + (size_t) antenna * h->T, (size_t) h->T * 4, cudaMemcpyDeviceToHost));
+    for (int t = 0; t < h->T; ++t)
+      if (mk[t] == 0)
+        CK (cudaMemcpy (out + (size_t) t * 2 * VF_NCHANOUT, s->P_raw + off + (size_t) t * VF_NCHANOUT,
+                        VF_NCHANOUT * sizeof (float2), cudaMemcpyDeviceToHost));
+  }
+  return VF_OK;
+}
+
+static float2 *vf_bp_of (vf_handle *h, int which)
+{
+  if (h->cfg.rfi_mode == 2) return which ? h->bp_raw : h->bp_kur;
+  return which ? NULL : h->bp_raw;
+}
+
+int vf_get_bandpass (vf_handle *h, int antenna, int which, float *out)
+{
+  int rc = vf_check_ant (h, antenna);
+  if (rc) return rc;
+  float2 *bp = (out && which >= 0 && which <= 1) ? vf_bp_of (h, which) : NULL;
+  if (!bp) return vf_fail (h, VF_ERR_ARG, "no such bandpass");
+  rc = vf_sync (h);
+  if (rc) return rc;
+  std::vector<float2> tmp (VF_NCHANOUT);
+  CK (cudaMemcpy (tmp.data (), bp + (size_t) antenna * VF_NCHANOUT, VF_NCHANOUT * sizeof (float2), cudaMemcpyDeviceToHost));
+  for (int c = 0; c < VF_NCHANOUT; ++c) { out[c] = tmp[c].x; out[VF_NCHANOUT + c] = tmp[c].y; }
+  return VF_OK;
+}
+
+int vf_set_bandpass (vf_handle *h, int antenna, int which, const float *in)
+{
+  int rc = vf_check_ant (h, antenna);
+  if (rc) return rc;
+  float2 *bp = (in && which >= 0 && which <= 1) ? vf_bp_of (h, which) : NULL;
+  if (!bp) return vf_fail (h, VF_ERR_ARG, "no such bandpass");
+  rc = vf_sync (h);
+  if (rc) return rc;
+  std::vector<float2> tmp (VF_NCHANOUT);
+  for (int c = 0; c < VF_NCHANOUT; ++c) tmp[c] = make_float2 (in[c], in[VF_NCHANOUT + c]);
+  CK (cudaMemcpy (bp + (size_t) antenna * VF_NCHANOUT, tmp.data (), VF_NCHANOUT * sizeof (float2), cudaMemcpyHostToDevice));
+  return VF_OK;
+}
+
+int vf_reset_bandpass (vf_handle *h, int antenna)
+{
+  if (!h) return VF_ERR_ARG;
+  if (antenna >= h->n_ant) return vf_fail (h, VF_ERR_ARG, "antenna %d outside 0..%d", antenna, h->n_ant - 1);
+  int rc = vf_sync (h);
+  if (rc) return rc;
+  const size_t off = antenna < 0 ? 0 : (size_t) antenna * VF_NCHANOUT;
+  const size_t n = (antenna < 0 ? (size_t) h->n_ant : 1) * VF_NCHANOUT * sizeof (float2);
+  CK (cudaMemset (h->bp_raw + off, 0, n));
+  if (h->bp_kur) CK (cudaMemset (h->bp_kur + off, 0, n));
+  return VF_OK;
+}
+
+int vf_set_frb_injection (vf_handle *h, int nfft_since_frb, float dm, float width, float amp)
+{
+  if (!h) return VF_ERR_ARG;
+  if (!h->cfg.inject_frb) return vf_fail (h, VF_ERR_STATE, "handle created without inject_frb");
+  if (nfft_since_frb < 0) { h->frb_nfft_since = -1; return VF_OK; }
+  if (!h->frb_delays || dm != h->frb_dm) {
+    /* set_frb_delays, src/pb_kernels.cu:338-346, in the same double arithmetic */
+    std::vector<float> d (VF_NCHAN_FFT);
+    for (int i = 0; i < VF_NCHAN_FFT; ++i) {
+      double freq = 0.384 - (i * 0.064) / VF_NCHAN_FFT;
+      double scale = 4.15e-3 * dm * 10 * 128000000 / 10 / VF_NFFT;
+      d[i] = (float) (scale / (freq * freq) - scale / (0.384 * 0.384));
+    }
+    int rc = vf_sync (h);
+    if (rc) return rc;
+    if (!h->frb_delays) CK (cudaMalloc ((void **) &h->frb_delays, VF_NCHAN_FFT * sizeof (float)));
+    CK (cudaMemcpy (h->frb_delays, d.data (), VF_NCHAN_FFT * sizeof (float), cudaMemcpyHostToDevice));
+    h->frb_dm = dm;
+  }
+  h->frb_nfft_since = nfft_since_frb; h->frb_width = width; h->frb_amp = amp;
+  return VF_OK;
+}
+
+/* ---- co-add --------------------------------------------------------------- */
+static int vf_nccl_load (vf_handle *h)
+{
+  if (g_nccl.lib) return VF_OK;
+  const char *names[] = { "libnccl.so.2", "libnccl.so", NULL };
+  void *lib = NULL;
+  for (int i = 0; names[i] && !lib; ++i) lib = dlopen (names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return vf_fail (h, VF_ERR_NCCL, "cannot load libnccl: %s", dlerror ());
+  g_nccl.GetUniqueId = (int (*) (vf_nccl_id *)) dlsym (lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*) (vf_nccl_comm *, int, vf_nccl_id, int)) dlsym (lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*) (const void *, void *, size_t, int, int, vf_nccl_comm, cudaStream_t)) dlsym (lib, "ncclAllReduce");
+  g_nccl.Reduce = (int (*) (const void *, void *, size_t, int, int, int, vf_nccl_comm, cudaStream_t)) dlsym (lib, "ncclReduce");
+  g_nccl.CommDestroy = (int (*) (vf_nccl_comm)) dlsym (lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char *(*) (int)) dlsym (lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.Reduce || !g_nccl.CommDestroy)
+    return vf_fail (h, VF_ERR_NCCL, "libnccl lacks a required symbol");
+  g_nccl.lib = lib;
+  return VF_OK;
+}
+
+int vf_coadd_unique_id (void *out128)
+{
+  if (!out128) return VF_ERR_ARG;
+  int rc = vf_nccl_load (NULL);
+  if (rc) return rc;
+  vf_nccl_id id;
+  if (g_nccl.GetUniqueId (&id) != 0) return VF_ERR_NCCL;
+  memcpy (out128, &id, 128);
+  return VF_OK;
+}
+
+int vf_coadd_init (vf_handle *h, int nranks, int rank, const void *nccl_unique_id)
+{
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks) return VF_ERR_ARG;
+  if (!h->ave_main) return vf_fail (h, VF_ERR_STATE, "co-add needs keep_power");
+  CK (cudaSetDevice (h->cfg.gpu_id));
+  const size_t n = (size_t) h->cfg.npol * h->ntime * VF_NCHANOUT;
+  if (!h->coadd_sum) {
+    CK (cudaMalloc ((void **) &h->coadd_sum, n * sizeof (float)));
+    CK (cudaMalloc ((void **) &h->coadd_out, n * h->cfg.nbit / 8));
+  }
+  h->nranks = nranks; h->rank = rank;
+  if (nranks > 1) {
+    if (!nccl_unique_id) return vf_fail (h, VF_ERR_ARG, "nranks > 1 needs the NCCL unique id");
+    int rc = vf_nccl_load (h);
+    if (rc) return rc;
+    vf_nccl_id id;
+    memcpy (&id, nccl_unique_id, 128);
+    int e = g_nccl.CommInitRank (&h->comm, nranks, id, rank);
+    if (e != 0) return vf_fail (h, VF_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString (e) : "?");
+  }
+  return VF_OK;
+}
+
+int vf_coadd_segment (vf_handle *h, int root, int total_antennas, uint8_t *fb_coadd, float *sum_f32)
+{
+  if (!h || total_antennas < 1) return VF_ERR_ARG;
+  if (!h->coadd_sum) return vf_fail (h, VF_ERR_STATE, "vf_coadd_init not called");
+  if (root < 0 || root >= (h->nranks ? h->nranks : 1)) return vf_fail (h, VF_ERR_ARG, "bad root");
+  CK (cudaSetDevice (h->cfg.gpu_id));
+  const size_t n = (size_t) h->cfg.npol * h->ntime * VF_NCHANOUT;
+  cudaStream_t st = h->ctl;
+  /* after every K2 that wrote the tiles */
+  if (h->have_k2_last) CK (cudaStreamWaitEvent (st, h->ev_k2_last, 0));
+  CK (cudaMemcpyAsync (h->coadd_sum, h->ave_main, n * sizeof (float), cudaMemcpyDeviceToDevice, st));
+  for (int a = 1; a < h->n_ant; ++a)
+    CK (vf_launch_accum (h->coadd_sum, h->ave_main + (size_t) a * n, n, st));
+  if (h->nranks > 1) {
+    /* ncclFloat32 = 7, ncclSum = 0 (nccl.h) */
+    int e = g_nccl.Reduce (h->coadd_sum, h->coadd_sum, n, 7, 0, root, h->comm, st);
+    if (e != 0) return vf_fail (h, VF_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString (e) : "?");
+  }
+  if (h->rank == root) {
+    vf_coadd_params cp;
+    cp.sum = h->coadd_sum; cp.cnt = NULL;
+    cp.scale = (float) (1.0 / sqrt ((double) total_antennas));
+    cp.ntime = h->ntime; cp.npol = h->cfg.npol; cp.nbit = h->cfg.nbit; cp.out = h->coadd_out;
+    CK (vf_launch_coadd (cp, st));
+    if (fb_coadd) CK (cudaMemcpyAsync (fb_coadd, h->coadd_out, n * h->cfg.nbit / 8, cudaMemcpyDeviceToHost, st));
+    if (sum_f32) CK (cudaMemcpyAsync (sum_f32, h->coadd_sum, n * sizeof (float), cudaMemcpyDeviceToHost, st));
+  }
+  CK (cudaStreamSynchronize (st));
+  return VF_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,81 @@
+/*
+ * Internal kernel interface of libvlitefast (not part of the C ABI).
+ * Geometry follows src/process_baseband.h:16-55 of the reference.
+ */
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "vf_fft12500.cuh"
+
+#define VF_NCHAN_FFT   6251     /* NFFT/2+1, src/process_baseband.h:22 */
+#define VF_NSCRUNCH    8        /* :24 */
+#define VF_NKURTO      500      /* :35 */
+#define VF_NSUB        25       /* NFFT/NKURTO */
+#define VF_CHANMIN     2155     /* :53 */
+#define VF_CHANMAX     6250     /* :54 */
+#define VF_NCHANOUT    4096
+#define VF_VD_FRM      5032     /* :16 */
+#define VF_VD_DAT      5000     /* :17 */
+#define VF_FRAME_RATE  25600    /* :19 */
+
+#define VF_WIN         12512    /* 16-byte aligned window that covers any 12500-sample block */
+
+/* Channeliser: one work item = one FFT time step of one antenna (both pols). */
+struct vf_k1_params {
+  const uint8_t *in;          /* [n_ant][2][T*12500] samples, every pol 16-byte aligned */
+  size_t ant_stride, pol_stride;
+  int T, n_ant, rfi_mode;
+  float2 *P_raw, *P_kur;      /* [n_ant][T][4096] (pol0, pol1) detected power */
+  float *w;                   /* [n_ant][T] excision weight (shared by both pols) */
+  uint32_t *mask;             /* [n_ant][T] bit j = sub-block j zeroed */
+  float *pw, *kur, *dag;      /* optional [n_ant][2][T*25] */
+  float *pw_fb, *kur_fb, *dag_fb;  /* optional [n_ant][2][T] */
+  unsigned int *histo;        /* optional [n_ant][2][256] */
+  vf_fft_tables tb;
+  double dagc[5], dagc_fb[5]; /* mu1, A, Z1, Z2, Z3 for N = 500 and N = 12500 */
+  const float *wtab;          /* [26] device: k-fold float sum of float(500)/12500 */
+  const float *frb_delays;    /* optional [6251]; FRB injection, src/pb_kernels.cu:348-391 */
+  int nfft_since_frb;
+  float frb_width, frb_amp;
+  unsigned int *work_counter; /* dynamic work distribution */
+};
+
+/* Normaliser: bandpass IIR + pscrunch + tscrunch + select/digitise. */
+struct vf_k2_params {
+  const float2 *P_raw, *P_kur;
+  const float *w;
+  const uint32_t *mask;
+  float2 *bp_raw, *bp_kur;    /* [n_ant][4096] running bandpass (pol0, pol1) */
+  int T, n_ant, rfi_mode, npol, nbit;
+  float bp_scale;
+  uint8_t *out_main, *out_raw;/* [n_ant][out_bytes] */
+  size_t out_stride;
+  float *ave_main, *ave_raw;  /* optional [n_ant][npol][T/8][4096] */
+};
+
+struct vf_depack_params {
+  const uint8_t *frames;      /* [nframes][5032] */
+  size_t nframes;
+  uint8_t *out;               /* [2][T*12500] */
+  size_t pol_stride;
+  long long frame0;           /* frame number (within second) of sample 0 of out */
+  long long nframes_per_pol;  /* frames that fit in out */
+  unsigned int *bad;          /* count of frames outside the window */
+};
+
+struct vf_coadd_params {
+  const float *sum;           /* [npol][T/8][4096] summed tiles */
+  const float *cnt;           /* optional same shape: contributing antennas, else NULL */
+  float scale;                /* 1/sqrt(n_ant) when cnt == NULL */
+  int ntime, npol, nbit;
+  uint8_t *out;
+};
+
+cudaError_t vf_launch_k1 (const vf_k1_params &p, int grid, int threads, cudaStream_t s);
+cudaError_t vf_launch_k2 (const vf_k2_params &p, cudaStream_t s);
+cudaError_t vf_launch_depack (const vf_depack_params &p, cudaStream_t s);
+cudaError_t vf_launch_coadd (const vf_coadd_params &p, cudaStream_t s);
+cudaError_t vf_launch_accum (float *dst, const float *src, size_t n, cudaStream_t s);
+size_t vf_k1_smem_bytes (void);
+cudaError_t vf_k1_configure (void);
