@@ -42,9 +42,11 @@ def test_segment_matches_oracle(pkg, orc, mode, nbit, npol):
         assert np.array_equal(p.get_mask(), o.mask())
         st = p.get_stats()
         assert np.count_nonzero(p.get_mask()) > 0
-        for k in ("pow", "kur", "dag", "pow_fb", "kur_fb", "weights"):
+        for k in ("pow", "kur", "pow_fb", "kur_fb", "weights"):
             assert np.array_equal(st[k], o.get(k), equal_nan=True), k
-        np.testing.assert_allclose(st["dag_fb"], o.get("dag_fb"), rtol=1e-6)
+        # powf is the one operation that differs between glibc (oracle) and libdevice (GPU)
+        np.testing.assert_allclose(st["dag"], o.get("dag"), rtol=1e-5, atol=5e-6)
+        np.testing.assert_allclose(st["dag_fb"], o.get("dag_fb"), rtol=1e-5, atol=2e-5)
         assert np.array_equal(st["histo"], o.get("histo"))
     det, odet = p.get_detected_power(0, 0), o.power_trimmed("main")
     assert np.abs(det - odet).max() / odet.mean() < REL

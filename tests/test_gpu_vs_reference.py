@@ -55,7 +55,7 @@ def test_cpu_oracle_vs_reference_kernels(pkg, orc):
     for k in ("pow", "kur", "pow_fb", "kur_fb", "weights", "histo"):
         assert np.array_equal(o.get(k), r.get(k), equal_nan=True), k
     # powf differs by a few ulp between glibc and libdevice
-    np.testing.assert_allclose(o.get("dag"), r.get("dag"), rtol=2e-6)
+    np.testing.assert_allclose(o.get("dag"), r.get("dag"), rtol=1e-5, atol=5e-6)
     assert np.array_equal(o.mask(), r.mask())
     odet, rdet = o.power_trimmed("main"), r.power_trimmed("main")
     assert np.abs(odet - rdet).max() / rdet.mean() < REL
@@ -72,10 +72,12 @@ def test_frb_injection_vs_reference(pkg, orc):
     with pkg.Pipeline(ffts_per_seg=T, nbit=8, npol=1, rfi_mode=0, inject_frb=1) as p:
         plain, _ = p.process_segment(p0, p1)
         p.reset_bandpass()
-        p.set_frb_injection(0, 80.0, 20.48, 1.05)      # first segment of the FRB second
+        # the DM 80 sweep reaches the kept channels (bins >= 2155) ~2900 FFT steps after
+        # the FRB second starts: third segment, nfft_since_frb = 2 * 1024
+        p.set_frb_injection(2048, 80.0, 20.48, 1.05)
         inj, _ = p.process_segment(p0, p1)
         det = p.get_detected_power(0, 0)
-    rinj, _ = r.process_segment(p0, p1, inject_frb_now=1)
+    rinj, _ = r.process_segment(p0, p1, inject_frb_now=3)
     rdet = r.power_trimmed("main")
     assert not np.array_equal(plain, inj)
     assert np.abs(det - rdet).max() / rdet.mean() < REL

@@ -82,6 +82,7 @@ struct vf_handle {
   /* co-add */
   vf_nccl_comm comm; int nranks, rank;
   float *coadd_sum; uint8_t *coadd_out;
+  int debug_sync;
   char err[512];
 };
 
@@ -233,6 +234,7 @@ int vf_create (const vf_config *cfg, vf_handle **out)
   h->out_bytes = (size_t) h->ntime * cfg->npol * VF_NCHANOUT * cfg->nbit / 8;
   h->tile_elems = (size_t) h->T * VF_NCHANOUT;
   h->frb_nfft_since = -1;
+  { const char *e = getenv ("VF_DEBUG_SYNC"); h->debug_sync = e && *e == '1'; }
 
   CK (cudaSetDevice (cfg->gpu_id));
   cudaDeviceProp prop;
@@ -354,6 +356,7 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
   const int threads = c.k1_threads ? c.k1_threads : 640;
   if (timed >= 0) CK (cudaEventRecord (h->ev_ka[timed], s->st));
   CK (vf_launch_k1 (k1, grid, threads, s->st));
+  if (h->debug_sync) CK (cudaStreamSynchronize (s->st));      /* VF_DEBUG_SYNC=1: attribute faults to a kernel */
   if (timed >= 0) CK (cudaEventRecord (h->ev_kb[timed], s->st));
 
   /* the bandpass makes K2 launches sequential in segment order */
@@ -368,6 +371,7 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
   k2.out_main = d_main; k2.out_raw = d_raw; k2.out_stride = h->out_bytes;
   k2.ave_main = h->ave_main; k2.ave_raw = h->ave_raw;
   CK (vf_launch_k2 (k2, s->st));
+  if (h->debug_sync) CK (cudaStreamSynchronize (s->st));
   if (timed >= 0) CK (cudaEventRecord (h->ev_kc[timed], s->st));
   CK (cudaEventRecord (h->ev_k2_last, s->st));
   h->have_k2_last = 1;
