@@ -51,7 +51,7 @@ typedef struct vf_config {
   int abi_version;     /* VF_ABI_VERSION                                           */
   int nfft;            /* 12500  NFFT (only value supported)                        */
   int nscrunch;        /* 8      NSCRUNCH                                           */
-  int ffts_per_seg;    /* 1024   FFTS_PER_SEG = 128e6/10/12500; multiple of 8       */
+  int ffts_per_seg;    /* 1024   FFTS_PER_SEG = 128e6/10/12500; multiple of 8, <= 8192 */
   int nkurto;          /* 500    NKURTO                                             */
   int chanmin;         /* 2155   CHANMIN                                            */
   int chanmax;         /* 6250   CHANMAX (chanmax-chanmin+1 must be 4096)           */
@@ -64,7 +64,7 @@ typedef struct vf_config {
   int inject_frb;      /* 0      -i: allow vf_set_frb_injection                     */
   int gpu_id;          /* 0      -g                                                 */
   int n_antennas;      /* 1      antennas batched on this handle                    */
-  int k1_threads;      /* 0      0 = library default; 320 or 640 (tuning)           */
+  int k1_threads;      /* 0      0 = library default (320); 320, 512 or 640 (tuning) */
   int reserved[7];
 } vf_config;
 

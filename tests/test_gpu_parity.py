@@ -212,3 +212,14 @@ def test_coadd_single_process(pkg, orc):
     want = np.empty(fb.size, np.uint8)
     orc.liba().orc_digitise(full.ctypes.data, want.ctypes.data, T // 8, 1, 8)
     check_bytes(fb, want, 8, "coadd")
+
+
+@pytest.mark.parametrize("T,nbit,npol", [(8, 2, 1), (24, 4, 2), (72, 2, 2), (136, 8, 1)])
+def test_ragged_segment_lengths(pkg, orc, T, nbit, npol):
+    """segment lengths that are not a multiple of the normaliser's 64-step chunk"""
+    p, o, res = run_both(pkg, orc, T, nbit, npol, 2, seed=T, nseg=2, **RFI)
+    for (main, raw), (omain, oraw) in res:
+        check_bytes(main, omain, nbit, "main")
+        check_bytes(raw, oraw, nbit, "raw")
+    assert np.array_equal(p.get_mask(), o.mask())
+    p.close()

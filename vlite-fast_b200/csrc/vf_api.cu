@@ -212,12 +212,12 @@ int vf_create (const vf_config *cfg, vf_handle **out)
    * src/process_baseband.h:16-55); sanity checks of :535-538, :667-672 */
   if (cfg->nfft != VF_NFFT || cfg->nscrunch != VF_NSCRUNCH || cfg->nkurto != VF_NKURTO) return VF_ERR_ARG;
   if (cfg->chanmin != VF_CHANMIN || cfg->chanmax != VF_CHANMAX) return VF_ERR_ARG;
-  if (cfg->ffts_per_seg <= 0 || cfg->ffts_per_seg % VF_NSCRUNCH) return VF_ERR_ARG;
+  if (cfg->ffts_per_seg <= 0 || cfg->ffts_per_seg % VF_NSCRUNCH || cfg->ffts_per_seg > 8192) return VF_ERR_ARG;
   if (!(cfg->nbit == 2 || cfg->nbit == 4 || cfg->nbit == 8)) return VF_ERR_ARG;
   if (!(cfg->npol == 1 || cfg->npol == 2)) return VF_ERR_ARG;
   if (cfg->rfi_mode < 0 || cfg->rfi_mode > 2) return VF_ERR_ARG;
   if (cfg->n_antennas < 1 || cfg->n_antennas > 4096) return VF_ERR_ARG;
-  if (!(cfg->k1_threads == 0 || cfg->k1_threads == 320 || cfg->k1_threads == 640)) return VF_ERR_ARG;
+  if (!(cfg->k1_threads == 0 || cfg->k1_threads == 320 || cfg->k1_threads == 512 || cfg->k1_threads == 640)) return VF_ERR_ARG;
 
   int ndev = 0;
   if (cudaGetDeviceCount (&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError (); return VF_ERR_NODEV; }
@@ -353,7 +353,7 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
   if (h->histo) CK (cudaMemsetAsync (h->histo, 0, (size_t) n_ant * 512 * sizeof (unsigned int), s->st));
   const int n_items = n_ant * h->T;
   const int grid = n_items < h->nsm ? n_items : h->nsm;
-  const int threads = c.k1_threads ? c.k1_threads : 640;
+  const int threads = c.k1_threads ? c.k1_threads : 320;
   if (timed >= 0) CK (cudaEventRecord (h->ev_ka[timed], s->st));
   CK (vf_launch_k1 (k1, grid, threads, s->st));
   if (h->debug_sync) CK (cudaStreamSynchronize (s->st));      /* VF_DEBUG_SYNC=1: attribute faults to a kernel */
