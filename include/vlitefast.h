@@ -116,6 +116,11 @@ int vf_submit_async (vf_handle *h, int slot, int n_ant,
                      const uint8_t *const *pol0, const uint8_t *const *pol1, size_t nsamp_per_pol,
                      uint8_t *const *fb_main, uint8_t *const *fb_raw);
 int vf_wait (vf_handle *h, int slot);
+/* Asynchronous form of vf_process_vdif: the frames are DMA'd straight from the
+ * caller's (pinned) memory -- e.g. a block of the input ring -- and must stay
+ * valid until vf_wait (slot), which also reports frames outside the window. */
+int vf_submit_vdif_async (vf_handle *h, int slot, int antenna, const void *frames, size_t nframes,
+                          uint32_t first_frame, uint8_t *fb_main, uint8_t *fb_raw);
 
 /* Device-resident form: d_in is [n_ant][2][ffts_per_seg*12500] bytes on the
  * device (256-byte aligned), d_fb_main / d_fb_raw [n_ant][out_bytes].  Enqueued

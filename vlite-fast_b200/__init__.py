@@ -10,6 +10,7 @@ The directory name carries a hyphen (it mirrors the reference's name), so it
 is loaded through ``__graft_entry__.load_package()`` under the module name
 ``vlite_fast_b200``.
 """
+from .sharding import antennas_of_rank, coadd_scale
 from .binding import (VfConfig, Pipeline, VfError, lib, hostlib, GenParams, gen_samples,
                       gen_vdif_second, NFFT, NCHANOUT, NSCRUNCH, NSUB, VD_FRM, VD_DAT,
                       FRAMES_PER_SEC)

@@ -63,6 +63,7 @@ def lib():
     L.vf_process_vdif.argtypes = [vp, i, vp, sz, C.c_uint32, u8p, u8p, C.POINTER(sz)]
     L.vf_submit_async.argtypes = [vp, i, i, pp, pp, sz, pp, pp]
     L.vf_wait.argtypes = [vp, i]
+    L.vf_submit_vdif_async.argtypes = [vp, i, i, vp, sz, C.c_uint32, u8p, u8p]
     L.vf_process_device.argtypes = [vp, i, i, vp, vp, vp]
     L.vf_sync.argtypes = [vp]
     fp = C.POINTER(C.c_float)

@@ -36,7 +36,9 @@ struct vf_slot {
   uint32_t *mask;             /* [n_ant][T] */
   uint8_t *d_out_main, *d_out_raw;   /* [n_ant][out_bytes] */
   cudaEvent_t ev_k2, ev_done;
-  int pending;                /* vf_submit_async issued, vf_wait not yet called */
+  int pending;                /* vf_submit_*_async issued, vf_wait not yet called */
+  unsigned int *d_bad, *h_bad;/* frames outside the window (VDIF input) */
+  uint32_t first_frame;
 };
 
 /* minimal NCCL surface, resolved with dlopen at vf_coadd_init */
@@ -73,7 +75,6 @@ struct vf_handle {
   float *ave_main, *ave_raw;  /* [n_ant][npol][T/8][4096] */
   float *frb_delays;
   int frb_nfft_since; float frb_width, frb_amp; float frb_dm;
-  unsigned int *d_bad, *h_bad;
   double dagc[5], dagc_fb[5];
   /* timing */
   cudaEvent_t ev_t0, ev_t1;
@@ -182,14 +183,14 @@ int vf_destroy (vf_handle *h)
     vf_slot *s = &h->slot[i];
     cudaFree (s->d_in); cudaFree (s->d_frames); cudaFree (s->P_raw); cudaFree (s->P_kur);
     cudaFree (s->w); cudaFree (s->mask); cudaFree (s->d_out_main); cudaFree (s->d_out_raw);
+    cudaFree (s->d_bad); if (s->h_bad) cudaFreeHost (s->h_bad);
     if (s->ev_k2) cudaEventDestroy (s->ev_k2);
     if (s->ev_done) cudaEventDestroy (s->ev_done);
     if (s->st) cudaStreamDestroy (s->st);
   }
   cudaFree (h->bp_raw); cudaFree (h->bp_kur); cudaFree (h->tw); cudaFree (h->wtab);
   cudaFree (h->pw); cudaFree (h->pw_fb); cudaFree (h->histo); cudaFree (h->ave_main); cudaFree (h->ave_raw);
-  cudaFree (h->frb_delays); cudaFree (h->d_bad); cudaFree (h->coadd_sum); cudaFree (h->coadd_out);
-  if (h->h_bad) cudaFreeHost (h->h_bad);
+  cudaFree (h->frb_delays); cudaFree (h->coadd_sum); cudaFree (h->coadd_out);
   if (h->ev_t0) cudaEventDestroy (h->ev_t0);
   if (h->ev_t1) cudaEventDestroy (h->ev_t1);
   if (h->ev_k2_last) cudaEventDestroy (h->ev_k2_last);
@@ -302,8 +303,6 @@ int vf_create (const vf_config *cfg, vf_handle **out)
       CK (cudaMemset (h->ave_raw, 0, n * sizeof (float)));
     }
   }
-  CK (cudaMalloc ((void **) &h->d_bad, sizeof (unsigned int)));
-  CK (cudaMallocHost ((void **) &h->h_bad, sizeof (unsigned int)));
   CK (cudaEventCreate (&h->ev_t0));
   CK (cudaEventCreate (&h->ev_t1));
   CK (cudaEventCreateWithFlags (&h->ev_k2_last, cudaEventDisableTiming));
@@ -450,8 +449,11 @@ int vf_wait (vf_handle *h, int slot)
   if (!h || slot < 0 || slot > 1) return VF_ERR_ARG;
   vf_slot *s = &h->slot[slot];
   if (!s->pending) return vf_fail (h, VF_ERR_STATE, "vf_wait (%d) without vf_submit_async", slot);
+  const int kind = s->pending;
   s->pending = 0;
   CK (cudaEventSynchronize (s->ev_done));
+  if (kind == 2 && *s->h_bad)
+    return vf_fail (h, VF_ERR_VDIF, "%u frame(s) outside the segment starting at frame %u", *s->h_bad, s->first_frame);
   return VF_OK;
 }
 
@@ -486,16 +488,16 @@ int vf_process_segment (vf_handle *h, int antenna,
   return rc;
 }
 
-int vf_process_vdif (vf_handle *h, int antenna, const void *frames, size_t nframes,
-                     uint32_t first_frame, uint8_t *fb_main, uint8_t *fb_raw, size_t *nbytes)
+int vf_submit_vdif_async (vf_handle *h, int slot, int antenna, const void *frames, size_t nframes,
+                          uint32_t first_frame, uint8_t *fb_main, uint8_t *fb_raw)
 {
   if (!h || !frames || !fb_main) return VF_ERR_ARG;
-  if (antenna != 0) return vf_fail (h, VF_ERR_ARG, "vf_process_vdif drives antenna 0 of the handle");
+  if (slot < 0 || slot > 1) return vf_fail (h, VF_ERR_ARG, "bad slot");
+  if (antenna != 0) return vf_fail (h, VF_ERR_ARG, "the VDIF entry points drive antenna 0 of the handle");
   const size_t per_pol = h->nsamp / VF_VD_DAT;            /* frames per pol per segment */
   if (nframes > 4 * per_pol) return vf_fail (h, VF_ERR_ARG, "%zu frames for a segment of %zu", nframes, 2 * per_pol);
-  const int slot = h->next_slot;
   vf_slot *s = &h->slot[slot];
-  if (s->pending) return vf_fail (h, VF_ERR_STATE, "slot %d has an asynchronous segment in flight", slot);
+  if (s->pending) return vf_fail (h, VF_ERR_STATE, "slot %d submitted twice without vf_wait", slot);
   CK (cudaSetDevice (h->cfg.gpu_id));
   const size_t bytes = nframes * VF_VD_FRM;
   if (s->frames_cap < bytes) {
@@ -504,32 +506,48 @@ int vf_process_vdif (vf_handle *h, int antenna, const void *frames, size_t nfram
     CK (cudaMalloc ((void **) &s->d_frames, cap));
     s->frames_cap = cap;
   }
-  int rc = vf_timing_begin (h, 0);
-  if (rc) return rc;
+  if (!s->d_bad) {
+    CK (cudaMalloc ((void **) &s->d_bad, sizeof (unsigned int)));
+    CK (cudaMallocHost ((void **) &s->h_bad, sizeof (unsigned int)));
+  }
   CK (cudaMemcpyAsync (s->d_frames, frames, bytes, cudaMemcpyHostToDevice, s->st));
   /* frames the writer never delivered stay zero, i.e. "dropped" samples
    * (src/writer.c:362,674-687; byte 0 -> 0.0, src/pb_kernels.cu:28-29) */
   CK (cudaMemsetAsync (s->d_in, 0, 2 * h->nsamp, s->st));
-  CK (cudaMemsetAsync (h->d_bad, 0, sizeof (unsigned int), s->st));
+  CK (cudaMemsetAsync (s->d_bad, 0, sizeof (unsigned int), s->st));
   vf_depack_params dp;
   dp.frames = s->d_frames; dp.nframes = nframes; dp.out = s->d_in; dp.pol_stride = h->nsamp;
-  dp.frame0 = first_frame; dp.nframes_per_pol = (long long) per_pol; dp.bad = h->d_bad;
+  dp.frame0 = first_frame; dp.nframes_per_pol = (long long) per_pol; dp.bad = s->d_bad;
   CK (vf_launch_depack (dp, s->st));
-  CK (cudaMemcpyAsync (h->h_bad, h->d_bad, sizeof (unsigned int), cudaMemcpyDeviceToHost, s->st));
-  rc = vf_enqueue_segment (h, s, 1, s->d_in, s->d_out_main, s->d_out_raw, -1);
+  CK (cudaMemcpyAsync (s->h_bad, s->d_bad, sizeof (unsigned int), cudaMemcpyDeviceToHost, s->st));
+  int rc = vf_enqueue_segment (h, s, 1, s->d_in, s->d_out_main, s->d_out_raw, -1);
   if (rc) return rc;
   CK (cudaMemcpyAsync (fb_main, s->d_out_main, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
   if (h->cfg.rfi_mode == 2 && fb_raw)
     CK (cudaMemcpyAsync (fb_raw, s->d_out_raw, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
-  rc = vf_timing_end (h);
-  if (rc) return rc;
-  CK (cudaStreamSynchronize (h->ctl));
+  CK (cudaEventRecord (s->ev_done, s->st));
+  s->pending = 2;               /* 2: vf_wait also reports frames outside the window */
+  s->first_frame = first_frame;
   h->last_slot = slot;
-  h->next_slot ^= 1;
-  if (nbytes) *nbytes = h->out_bytes;
-  if (*h->h_bad)
-    return vf_fail (h, VF_ERR_VDIF, "%u frame(s) outside the segment starting at frame %u", *h->h_bad, first_frame);
   return VF_OK;
+}
+
+int vf_process_vdif (vf_handle *h, int antenna, const void *frames, size_t nframes,
+                     uint32_t first_frame, uint8_t *fb_main, uint8_t *fb_raw, size_t *nbytes)
+{
+  if (!h) return VF_ERR_ARG;
+  const int slot = h->next_slot;
+  if (h->slot[slot].pending) return vf_fail (h, VF_ERR_STATE, "slot %d has an asynchronous segment in flight", slot);
+  int rc = vf_timing_begin (h, 0);
+  if (rc) return rc;
+  rc = vf_submit_vdif_async (h, slot, antenna, frames, nframes, first_frame, fb_main, fb_raw);
+  if (rc) return rc;
+  rc = vf_timing_end (h);
+  if (rc) { h->slot[slot].pending = 0; return rc; }
+  h->next_slot ^= 1;
+  rc = vf_wait (h, slot);
+  if (rc == VF_OK && nbytes) *nbytes = h->out_bytes;
+  return rc;
 }
 
 int vf_process_device (vf_handle *h, int n_ant, int n_seg, const uint8_t *d_in,

@@ -1,0 +1,369 @@
+/*
+ * process_baseband -- host driver of the baseband -> filterbank chain.
+ *
+ * Plain-C counterpart of the reference's main() (src/process_baseband.cu:334-
+ * 1615): command-line flags (:45-63, :358-470), wait for an observation header
+ * on the input ring (:799-832), check the alignment of the first VDIF frame
+ * (:837-849), open the SIGPROC files (:852-998), then per second of data ten
+ * 100 ms segments through the GPU (:1108-1458), log the processing rate
+ * (:1461-1477, :1534-1536).  All signal processing is in libvlitefast
+ * (include/vlitefast.h); this file only moves frames and bytes.
+ *
+ * Differences from the reference, all deliberate:
+ *  - psrdada is not available: the input ring is the in-process shim of
+ *    vf_ring.h, fed by a thread that replays a VDIF file (-f, the reference's
+ *    readbase) or synthetic seconds (-S, the reference's genbase);
+ *  - frames are not depacketised on the host (:1034-1035): one-second ring
+ *    blocks live in pinned memory and each segment is DMA'd straight from the
+ *    block and depacketised on the GPU (vf_submit_vdif_async), double buffered;
+ *  - the final complete second of an observation is processed (the reference
+ *    dispatches second N only when a frame of N+1 arrives, :1022-1067, and so
+ *    drops it).
+ */
+#define _GNU_SOURCE
+#include <errno.h>
+#include <getopt.h>
+#include <pthread.h>
+#include <signal.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+#include "vlitefast.h"
+#include "vf_genbase.h"
+#include "vf_ring.h"
+#include "vf_sigproc.h"
+#include "vf_vdif.h"
+
+#define SEG_PER_SEC 10
+#define FRAMES_PER_SEC_2POL (2 * VF_FRAME_RATE)                 /* 51200 */
+#define SEC_BYTES ((size_t) FRAMES_PER_SEC_2POL * VF_VD_FRM)    /* 257 638 400, scripts/start_writer:12 */
+
+static volatile sig_atomic_t g_quit = 0;
+static FILE *g_log = NULL;
+static int g_stdout = 0;
+
+static void on_signal (int sig) { (void) sig; g_quit = 1; }
+
+static void logmsg (const char *level, const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start (ap, fmt);
+  vsnprintf (buf, sizeof (buf), fmt, ap);
+  va_end (ap);
+  time_t now = time (NULL);
+  struct tm tm;
+  gmtime_r (&now, &tm);
+  char ts[32];
+  strftime (ts, sizeof (ts), "%Y-%m-%d-%H:%M:%S", &tm);
+  if (g_log) { fprintf (g_log, "[%s] %s %s", ts, level, buf); fflush (g_log); }
+  if (g_stdout || !g_log) { fprintf (stderr, "[%s] %s %s", ts, level, buf); }
+}
+
+static double now_s (void)
+{
+  struct timespec ts;
+  clock_gettime (CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static void usage (void)
+{
+  fprintf (stdout,
+    "Usage: process_baseband [options]\n"
+    "  -f FILE   replay a VDIF file into the input ring (readbase)\n"
+    "  -S N      synthesise N distinct seconds of baseband (genbase style) instead of -f\n"
+    "  -L M      replay the synthetic seconds M times (stream of N*M seconds) [1]\n"
+    "  -e SEED   generator seed [102];  -F  add impulsive RFI to the synthetic data\n"
+    "  -a ID     station id of the synthetic stream [1]\n"
+    "  -n NBUF   ring blocks of one second each [N for -S, else 4]\n"
+    "  -D DIR    directory of the output filterbank files [.]\n"
+    "  -w 0|1    write filterbank files [1]\n"
+    "  -b NBIT   2, 4 or 8 bit output [2]\n"
+    "  -P NPOL   1 (summed) or 2 polarisations [1]\n"
+    "  -r MODE   RFI excision: 0 off, 1 excised stream only, 2 both streams [2]\n"
+    "  -i        inject a DM 80 FRB every 60 s\n"
+    "  -s        process a single observation then quit\n"
+    "  -g GPU    CUDA device [0]\n"
+    "  -o        log to stderr as well\n"
+    "  -l FILE   log file\n"
+    "  -j        print a one-line JSON summary on stdout at exit\n");
+}
+
+typedef struct {
+  vf_ring *ring;
+  const char *file;
+  int synth_n, loops, station;
+  uint32_t second0;
+  int rc;
+} feeder_args;
+
+/* file -> ring, one frame-aligned block at a time (src/readbase.c:52-105) */
+static void *feeder_file (void *vp)
+{
+  feeder_args *a = (feeder_args *) vp;
+  FILE *fp = fopen (a->file, "rb");
+  if (!fp) { logmsg ("ERR", "cannot open %s: %s\n", a->file, strerror (errno)); a->rc = 1; vf_ring_shutdown (a->ring); return NULL; }
+  char hdr[VF_RING_HEADER_SIZE] = "";
+  /* the keys readbase sets, src/readbase.c:65-86 */
+  vf_ascii_header_set (hdr, sizeof (hdr), "NAME", "%s", "REPLAY");
+  vf_ascii_header_set (hdr, sizeof (hdr), "STATIONID", "%d", a->station);
+  vf_ascii_header_set (hdr, sizeof (hdr), "NCHAN", "%d", 1);
+  vf_ascii_header_set (hdr, sizeof (hdr), "BANDWIDTH", "%lf", -64.0);
+  vf_ascii_header_set (hdr, sizeof (hdr), "CFREQ", "%lf", 352.0);
+  vf_ascii_header_set (hdr, sizeof (hdr), "NPOL", "%d", 2);
+  vf_ascii_header_set (hdr, sizeof (hdr), "NBIT", "%d", 8);
+  vf_ascii_header_set (hdr, sizeof (hdr), "RA", "%lf", 0.87180);
+  vf_ascii_header_set (hdr, sizeof (hdr), "DEC", "%lf", 0.72452);
+  if (vf_ring_header_write (a->ring, hdr)) { fclose (fp); return NULL; }
+  for (;;) {
+    void *blk = vf_ring_block_write_open (a->ring);
+    if (!blk) break;
+    size_t n = fread (blk, 1, vf_ring_get_bufsz (a->ring), fp);
+    n -= n % VF_VD_FRM;
+    if (n == 0) { vf_ring_end_of_data (a->ring); break; }
+    vf_ring_block_write_close (a->ring, n);
+    if (g_quit) { vf_ring_end_of_data (a->ring); break; }
+  }
+  fclose (fp);
+  return NULL;
+}
+
+/* synthetic seconds already sit in the ring blocks (block b holds template
+ * second b % synth_n): publishing a block only needs its VDIF seconds patched */
+static void *feeder_synth (void *vp)
+{
+  feeder_args *a = (feeder_args *) vp;
+  char hdr[VF_RING_HEADER_SIZE] = "";
+  /* the keys genbase sets, src/genbase.cu:331-353 */
+  vf_ascii_header_set (hdr, sizeof (hdr), "NAME", "%s", "GENBASE");
+  vf_ascii_header_set (hdr, sizeof (hdr), "STATIONID", "%d", a->station);
+  vf_ascii_header_set (hdr, sizeof (hdr), "NCHAN", "%d", 1);
+  vf_ascii_header_set (hdr, sizeof (hdr), "BANDWIDTH", "%lf", -64.0);
+  vf_ascii_header_set (hdr, sizeof (hdr), "CFREQ", "%lf", 352.0);
+  vf_ascii_header_set (hdr, sizeof (hdr), "NPOL", "%d", 2);
+  vf_ascii_header_set (hdr, sizeof (hdr), "NBIT", "%d", 8);
+  vf_ascii_header_set (hdr, sizeof (hdr), "RA", "%lf", 0.87180);
+  vf_ascii_header_set (hdr, sizeof (hdr), "DEC", "%lf", 0.72452);
+  if (vf_ring_header_write (a->ring, hdr)) return NULL;
+  const long total = (long) a->synth_n * a->loops;
+  for (long s = 0; s < total && !g_quit; ++s) {
+    unsigned char *blk = (unsigned char *) vf_ring_block_write_open (a->ring);
+    if (!blk) return NULL;
+    const uint32_t sec = a->second0 + (uint32_t) s;
+    for (long f = 0; f < FRAMES_PER_SEC_2POL; ++f) {
+      uint32_t *w0 = (uint32_t *) (blk + (size_t) f * VF_VD_FRM);
+      *w0 = sec & 0x3FFFFFFFu;
+    }
+    vf_ring_block_write_close (a->ring, SEC_BYTES);
+  }
+  vf_ring_end_of_data (a->ring);
+  return NULL;
+}
+
+int main (int argc, char **argv)
+{
+  const char *file = NULL, *datadir = ".", *logfile = NULL;
+  int synth_n = 0, loops = 1, station = 1, nbuf = 0, write_fb = 1, single = 0, json = 0, rfi_flag = 0;
+  unsigned long long seed = 102;
+  vf_config cfg;
+  vf_config_default (&cfg);
+  int c;
+  while ((c = getopt (argc, argv, "hf:S:L:e:Fa:n:D:w:b:P:r:isg:ol:jk:K:C:p:")) != -1) {
+    switch (c) {
+      case 'h': usage (); return 0;
+      case 'f': file = optarg; break;
+      case 'S': synth_n = atoi (optarg); break;
+      case 'L': loops = atoi (optarg); break;
+      case 'e': seed = strtoull (optarg, NULL, 10); break;
+      case 'F': rfi_flag = 1; break;
+      case 'a': station = atoi (optarg); break;
+      case 'n': nbuf = atoi (optarg); break;
+      case 'D': datadir = optarg; break;
+      case 'w': write_fb = atoi (optarg); break;
+      case 'b': cfg.nbit = atoi (optarg);                         /* :415-426 */
+        if (!(cfg.nbit == 2 || cfg.nbit == 4 || cfg.nbit == 8)) { fprintf (stderr, "Unsupported NBIT!\n"); return 1; }
+        break;
+      case 'P': cfg.npol = atoi (optarg);                         /* :409-413 */
+        if (!(cfg.npol == 1 || cfg.npol == 2)) { fprintf (stderr, "Unsupported NPOL!\n"); return 1; }
+        break;
+      case 'r': cfg.rfi_mode = atoi (optarg);                     /* :427-437 */
+        if (cfg.rfi_mode < 0 || cfg.rfi_mode > 2) { fprintf (stderr, "Unsupported RFI mode!\n"); return 1; }
+        break;
+      case 'i': cfg.inject_frb = 1; break;
+      case 's': single = 1; break;
+      case 'g': cfg.gpu_id = atoi (optarg); break;
+      case 'o': g_stdout = 1; break;
+      case 'l': logfile = optarg; break;
+      case 'j': json = 1; break;
+      case 'k': case 'K': case 'C': case 'p': break;              /* psrdada keys / port of the reference: accepted, unused */
+      default: usage (); return 1;
+    }
+  }
+  if (!file && synth_n <= 0) { usage (); return 1; }
+  if (logfile) g_log = fopen (logfile, "a");
+  signal (SIGINT, on_signal);
+  signal (SIGTERM, on_signal);
+
+  vf_handle *h = NULL;
+  int rc = vf_create (&cfg, &h);
+  if (rc) {
+    logmsg ("ERR", "vf_create: %s (%s)\n", vf_strerror (rc), h ? vf_last_error (h) : "");
+    return 20;                                                    /* cudacheck's code, src/cuda_util.cu:10 */
+  }
+  const size_t out_bytes = vf_segment_out_bytes (h);
+
+  if (nbuf <= 0) nbuf = synth_n > 0 ? synth_n : 4;
+  if (synth_n > 0 && nbuf != synth_n) { logmsg ("ERR", "-n must equal -S for the in-place synthetic replay\n"); return 1; }
+  void *ring_mem = NULL;
+  if (vf_host_alloc (&ring_mem, (size_t) nbuf * SEC_BYTES)) { logmsg ("ERR", "cannot pin %d ring blocks\n", nbuf); return 21; }
+  vf_ring *ring = vf_ring_create ((uint64_t) nbuf, SEC_BYTES, ring_mem);
+  uint8_t *obuf[2][2] = {{NULL, NULL}, {NULL, NULL}};             /* [slot][main, raw] pinned */
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < 2; ++k)
+      if (vf_host_alloc ((void **) &obuf[s][k], out_bytes)) return 21;
+
+  if (synth_n > 0) {
+    /* templates straight into the ring blocks (not timed) */
+    vf_gen_params g;
+    vf_gen_defaults (&g);
+    g.seed = seed;
+    if (rfi_flag) { g.rfi_amp = 60; g.rfi_burst_every = 16; }
+    uint8_t *scratch = (uint8_t *) malloc (2 * (size_t) VF_VLITE_RATE);
+    if (!scratch) return 21;
+    for (int s = 0; s < synth_n; ++s)
+      vf_gen_vdif_block (&g, station, (uint32_t) s, scratch, (uint8_t *) ring_mem + (size_t) s * SEC_BYTES);
+    free (scratch);
+    logmsg ("INFO", "generated %d synthetic second(s), seed %llu\n", synth_n, seed);
+  }
+
+  feeder_args fa = { ring, file, synth_n, loops, station, 3600u * 5, 0 };
+  pthread_t feeder;
+  pthread_create (&feeder, NULL, file ? feeder_file : feeder_synth, &fa);
+
+  double total_data_s = 0, total_wall_s = 0;
+  long total_segments = 0;
+  int exit_status = 0;
+
+  while (!g_quit) {                                               /* observations, :784 */
+    char inhdr[VF_RING_HEADER_SIZE];
+    logmsg ("INFO", "Waiting for DADA header.\n");
+    int hr;
+    while ((hr = vf_ring_header_read (ring, inhdr, 200)) == 1 && !g_quit) ;
+    if (hr != 0) break;
+    logmsg ("INFO", "psrdada header:\n%s", inhdr);
+    logmsg ("INFO", "Beginning new observation.\n");
+    vf_obs_info obs;
+    vf_obs_info_from_header (inhdr, &obs);
+
+    FILE *fb_main = NULL, *fb_raw = NULL;
+    char fbfile[512] = "", fbfile_kur[512] = "";
+    const double t_obs = now_s ();
+    long seconds_done = 0, seg_counter = 0;
+    int first = 1, aborted = 0;
+    int pend_slot[2] = {0, 0};
+    vf_reset_bandpass (h, -1);    /* the reference keeps the bandpass across observations (:700-709); a new
+                                     stream here is a new antenna-time, so start clean */
+
+    for (;;) {                                                    /* seconds */
+      uint64_t nbytes = 0;
+      const unsigned char *blk = (const unsigned char *) vf_ring_block_read_open (ring, &nbytes);
+      if (!blk) break;                                            /* end of data: primary exit, :1044-1051 */
+      if (nbytes < SEC_BYTES) {
+        logmsg ("INFO", "Incomplete final second (%lu bytes), dropped.\n", (unsigned long) nbytes);
+        vf_ring_block_read_close (ring);
+        continue;
+      }
+      const vf_vdif_header *vh = (const vf_vdif_header *) blk;
+      if (first) {
+        if (vf_vdif_frame_number (vh) != 0 || vf_vdif_thread_id (vh) != 0) {     /* :843-849 */
+          logmsg ("ERR", "Incoming data were not aligned!\n");
+          exit_status = 1; aborted = 1;
+          vf_ring_block_read_close (ring);
+          break;
+        }
+        if (write_fb) {                                           /* :852-998 */
+          vf_fb_filename (fbfile, sizeof (fbfile), datadir, vh, obs.station_id, 0);
+          vf_fb_filename (fbfile_kur, sizeof (fbfile_kur), datadir, vh, obs.station_id, 1);
+          if (cfg.rfi_mode) {
+            fb_main = fopen (fbfile_kur, "wb");
+            if (cfg.rfi_mode == 2) fb_raw = fopen (fbfile, "wb");
+          } else
+            fb_main = fopen (fbfile, "wb");
+          if (!fb_main || (cfg.rfi_mode == 2 && !fb_raw)) { logmsg ("ERR", "cannot open output file in %s\n", datadir); exit_status = 1; aborted = 1; vf_ring_block_read_close (ring); break; }
+          vf_write_sigproc_header (fb_main, &obs, vh, cfg.nbit, cfg.npol);
+          if (fb_raw) vf_write_sigproc_header (fb_raw, &obs, vh, cfg.nbit, cfg.npol);
+          char dh[VF_RING_HEADER_SIZE];
+          vf_write_psrdada_header (dh, &obs, vh, cfg.nbit, cfg.npol, cfg.rfi_mode ? fbfile_kur : fbfile);
+          logmsg ("INFO", "output header:\n%s", dh);
+        }
+        logmsg ("INFO", "Starting sec=%d, thread=%d\n", vf_vdif_frame_second (vh), vf_vdif_thread_id (vh));
+        first = 0;
+      }
+      const int current_sec = vf_vdif_frame_second (vh);
+      const int inject_now = cfg.inject_frb && (current_sec % 60 == 0);          /* :1098-1101 */
+      if (inject_now) logmsg ("INFO", "Injecting an FRB!!!\n");
+
+      for (int iseg = 0; iseg < SEG_PER_SEC && !aborted; ++iseg, ++seg_counter) {  /* :1108 */
+        const int slot = (int) (seg_counter & 1);
+        if (pend_slot[slot]) {
+          rc = vf_wait (h, slot);
+          pend_slot[slot] = 0;
+          if (rc) { logmsg ("ERR", "segment failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; break; }
+          if (fb_main) fwrite (obuf[slot][0], 1, out_bytes, fb_main);              /* :1438-1441 */
+          if (fb_raw) fwrite (obuf[slot][1], 1, out_bytes, fb_raw);
+        }
+        if (cfg.inject_frb)
+          vf_set_frb_injection (h, inject_now ? iseg * 1024 : -1, 80.f, (float) (2e-3 * 10 * 1024), 1.05f);   /* :1238-1240 */
+        rc = vf_submit_vdif_async (h, slot, 0, blk + (size_t) iseg * (FRAMES_PER_SEC_2POL / SEG_PER_SEC) * VF_VD_FRM,
+                                   FRAMES_PER_SEC_2POL / SEG_PER_SEC, (uint32_t) (iseg * (VF_FRAME_RATE / SEG_PER_SEC)),
+                                   obuf[slot][0], obuf[slot][1]);
+        if (rc) { logmsg ("ERR", "submit failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; break; }
+        pend_slot[slot] = 1;
+      }
+      /* the block goes back to the writer: drain the two segments that still read from it */
+      for (int k = 0; k < 2; ++k) {
+        const int slot = (int) ((seg_counter + k) & 1);
+        if (!pend_slot[slot]) continue;
+        rc = vf_wait (h, slot);
+        pend_slot[slot] = 0;
+        if (rc) { logmsg ("ERR", "segment failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; continue; }
+        if (fb_main) fwrite (obuf[slot][0], 1, out_bytes, fb_main);
+        if (fb_raw) fwrite (obuf[slot][1], 1, out_bytes, fb_raw);
+      }
+      vf_ring_block_read_close (ring);
+      if (aborted) break;
+      seconds_done++;
+      if (seconds_done % 10 == 0) {                               /* RT_PROFILE watchdog, :1461-1477 */
+        const double wall = now_s () - t_obs;
+        if (wall - seconds_done > 0.5)
+          logmsg ("ERR", "Falling behind real time: %.2f s wall for %ld s of data.\n", wall, seconds_done);
+      }
+      if (g_quit) break;
+    }
+    if (fb_main) fclose (fb_main);
+    if (fb_raw) fclose (fb_raw);
+    const double wall = now_s () - t_obs;
+    logmsg ("INFO", "Proc Time...%.3f s for %ld s of data (%.1fx real time)\n", wall, seconds_done,
+            wall > 0 ? seconds_done / wall : 0.0);                /* :1534-1536 */
+    total_data_s += seconds_done; total_wall_s += wall; total_segments += seg_counter;
+    if (aborted) { vf_ring_shutdown (ring); break; }
+    if (single || synth_n > 0 || file) break;
+  }
+  vf_ring_shutdown (ring);
+  pthread_join (feeder, NULL);
+  if (json)
+    printf ("{\"program\": \"process_baseband\", \"seconds\": %.0f, \"segments\": %ld, \"wall_s\": %.6f, \"x_realtime\": %.3f, "
+            "\"nbit\": %d, \"npol\": %d, \"rfi_mode\": %d, \"bytes_in\": %.0f, \"exit\": %d}\n",
+            total_data_s, total_segments, total_wall_s, total_wall_s > 0 ? total_data_s / total_wall_s : 0.0,
+            cfg.nbit, cfg.npol, cfg.rfi_mode, total_data_s * (double) SEC_BYTES, exit_status | fa.rc);
+  vf_ring_destroy (ring);
+  for (int s = 0; s < 2; ++s) for (int k = 0; k < 2; ++k) vf_host_free (obuf[s][k]);
+  vf_host_free (ring_mem);
+  vf_destroy (h);
+  if (g_log) fclose (g_log);
+  return exit_status | fa.rc;
+}

@@ -104,3 +104,27 @@ size_t vf_gen_vdif_second (const vf_gen_params *g, int antenna, uint32_t second,
     }
   return (size_t) (p - out);
 }
+
+/* One full second (25600 frame pairs, 257 638 400 bytes) of antenna `antenna`:
+ * the samples of each pol are generated in one parallel sweep and then cut
+ * into frames (thread 0 then thread 1 per frame number, src/genbase.cu:443-486).
+ * scratch: 2 * 128 000 000 bytes.  Returns bytes written. */
+size_t vf_gen_vdif_block (const vf_gen_params *g, int antenna, uint32_t second, uint8_t *scratch, uint8_t *out)
+{
+  const size_t rate = 128000000;
+  for (int pol = 0; pol < 2; ++pol)
+    vf_gen_samples (g, antenna, pol, (uint64_t) second * rate, rate, scratch + (size_t) pol * rate);
+#pragma omp parallel for schedule(static)
+  for (long f = 0; f < 25600; ++f)
+    for (int th = 0; th < 2; ++th) {
+      uint8_t *p = out + ((size_t) f * 2 + th) * 5032;
+      uint32_t w[8] = {0};
+      w[0] = second & 0x3FFFFFFFu;
+      w[1] = ((uint32_t) f & 0xFFFFFFu) | (30u << 24);
+      w[2] = (5032u / 8) & 0xFFFFFFu;
+      w[3] = ((uint32_t) (antenna & 0xFFFF)) | ((uint32_t) th << 16) | (7u << 26);
+      memcpy (p, w, 32);
+      memcpy (p + 32, scratch + (size_t) th * rate + (size_t) f * 5000, 5000);
+    }
+  return (size_t) 25600 * 2 * 5032;
+}

@@ -32,6 +32,8 @@ void vf_gen_samples (const vf_gen_params *g, int antenna, int pol,
  * frame first_frame; 5032 bytes per frame.  Returns bytes written. */
 size_t vf_gen_vdif_second (const vf_gen_params *g, int antenna, uint32_t second,
                            uint32_t first_frame, uint32_t nframes, uint8_t *out);
+/* one full second of frames (257 638 400 bytes); scratch: 256 000 000 bytes */
+size_t vf_gen_vdif_block (const vf_gen_params *g, int antenna, uint32_t second, uint8_t *scratch, uint8_t *out);
 #ifdef __cplusplus
 }
 #endif
