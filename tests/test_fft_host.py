@@ -13,7 +13,7 @@ EXE = os.path.join(ROOT, "build", "vf_fft_hosttest")
 
 
 def run(b0, b1, mask=0):
-    r = subprocess.run([EXE, "%x" % mask], input=b0.tobytes() + b1.tobytes(), stdout=subprocess.PIPE, check=True)
+    r = subprocess.run([EXE, "%x" % mask, "0", "12499"], input=b0.tobytes() + b1.tobytes(), stdout=subprocess.PIPE, check=True)
     out = np.frombuffer(r.stdout, np.float32)
     P = out[: 2 * 4096].reshape(4096, 2)
     Z = out[2 * 4096:].reshape(12500, 2)

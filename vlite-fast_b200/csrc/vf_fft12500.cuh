@@ -7,19 +7,27 @@
  * of one time step in a single pass, and only the channels the filterbank keeps
  * (CHANMIN..CHANMAX, src/process_baseband.h:53-54) ever leave the SM.
  *
- * N = 12500 = 25 * 25 * 20, three Stockham autosort passes with the radix
- * butterflies held in registers:
+ * N = 12500 = 25 * 25 * 20, decimation in frequency, IN PLACE: every butterfly
+ * reads and writes the same shared-memory locations, so one barrier per pass
+ * is enough.  With n = 500 j + 20 j' + p'  and  k = k1 + 25 k2 + 625 k3:
  *
- *   pass A  radix 25, 500 butterflies  in  x[p + 500 j]        (8-bit samples)
- *                                      out y[25 p + k] * w_N^(p k)
- *   pass B  radix 25, 500 butterflies  in  x[i + 500 j],  i = q + 25 p
- *                                      out y[q + 625 p + 25 k] * w_500^(p k)
- *   pass C  radix 20, 625 butterflies  in  x[q + 625 j]
- *                                      out Z[q + 625 k]        (natural order)
+ *   pass 1  500 butterflies (p = 20 j' + p'), radix 25 over j
+ *           in   sample bytes x[500 j + p]          (unpack fused, mask = drop input j)
+ *           out  W[S k1 + p]  *=  w_N^(p k1)
+ *   pass 2  500 butterflies (k1, p'), radix 25 over j'
+ *           in/out  W[S k1 + 20 j' + p']  ->  W[S k1 + 20 k2 + p'] * w_500^(p' k2)
+ *   pass 3  625 butterflies (k1, k2), radix 20 over p'
+ *           in/out  W[S k1 + 20 k2 + p']  ->  W[S k1 + 20 k2 + k3]
  *
- * Every function here is __host__ __device__ and takes the butterfly index
- * explicitly, so tests/fft_hosttest.cu can run the exact index arithmetic of
- * the kernel on the CPU (one loop per pass where the kernel has a barrier).
+ * so Z[k] ends at  pos (k) = S (k mod 25) + 20 ((k / 25) mod 25) + k / 625.
+ * S = 501: the 500-element blocks are padded by one element so that threads
+ * which walk k1 (pass 3, detection) fall on distinct shared-memory banks.
+ * A 500-sample kurtosis block (src/pb_kernels.cu:243-295) is exactly input j of
+ * every pass-1 butterfly, so excision is "drop input j".
+ *
+ * Every function is __host__ __device__ and takes the butterfly index
+ * explicitly: csrc/vf_fft_hosttest.cu runs the same index arithmetic on the
+ * CPU (one loop per pass where the kernel has a barrier).
  */
 #pragma once
 #include <stdint.h>
@@ -31,8 +39,8 @@
 #define VF_HD inline
 #endif
 
-/* compiler-only fence: keeps ptxas from hoisting every twiddle load of a
- * butterfly above its arithmetic (register pressure at 640 threads per SM) */
+/* compiler-only fence: keeps ptxas from hoisting every load of a butterfly
+ * above its arithmetic (register pressure) */
 #if defined(__CUDA_ARCH__)
 #define VF_SCHED_FENCE() asm volatile ("" ::: "memory")
 #else
@@ -40,8 +48,10 @@
 #endif
 
 #define VF_NFFT      12500
-#define VF_NA        500     /* butterflies in passes A and B */
-#define VF_NC        625     /* butterflies in pass C */
+#define VF_NA        500     /* butterflies in passes 1 and 2 */
+#define VF_NC        625     /* butterflies in pass 3 */
+#define VF_WS        501     /* padded block stride of W */
+#define VF_WLEN      (25 * VF_WS)
 
 /* v *= (wr + i wi), compile-time constant */
 #define VF_CMULC(v, wr, wi) do { float _x = (v).x, _y = (v).y; \
@@ -107,117 +117,125 @@ VF_HD void vf_dft20 (float2 (&v)[20])
 }
 
 /* 8-bit sample -> voltage, src/pb_kernels.cu:23-33: 0 -> 0, else u/128 - 1.
- * 2^23 + u is built in the mantissa (no I2F); (2^23 + u)/128 - 65537 is exact. */
-VF_HD float vf_unpack (unsigned u)
+ * The staged bytes are "sanitised" first (0 -> 128, which is the same voltage
+ * 0.0), so the conversion is branch free: 2^23 + u is built in the mantissa
+ * (no I2F) and (2^23 + u)/128 - 65537 is exact. */
+VF_HD float vf_unpack_s (unsigned u)
 {
 #if defined(__CUDA_ARCH__)
   float v = __uint_as_float (0x4B000000u | u);
 #else
   float v = 8388608.0f + (float) u;
 #endif
-  float x = fmaf (v, 0.0078125f, -65537.0f);
-  return u ? x : 0.0f;
+  return fmaf (v, 0.0078125f, -65537.0f);
 }
 
-/* Twiddle tables (built on the host in double, rounded to float):
- *   tw1[p]  = w_12500^p        p < 500
- *   tw5[p]  = w_12500^(5 p)    p < 500
- *   tw500[m] = w_500^m         m < 500                                        */
-struct vf_fft_tables {
-  const float2 *tw1, *tw5, *tw500;
-};
-
-/* pass A: butterfly p in [0,500).  b0/b1 point at sample 0 of this FFT block
- * for pol 0 / pol 1.  Sub-block j of 500 samples (the kurtosis block,
- * src/pb_kernels.cu:243-295) is exactly input j of every butterfly, so the
- * excision mask is applied by dropping inputs. */
-VF_HD void vf_pass_a (int p, const uint8_t *b0, const uint8_t *b1, uint32_t zero_mask,
-                      const vf_fft_tables &tb, float2 *W)
+/* 0 -> 128 in every byte of a word */
+VF_HD uint32_t vf_sanitise_word (uint32_t w)
 {
-  float2 v[25];
-#pragma unroll
-  for (int j = 0; j < 25; ++j) {
-    float x0 = vf_unpack (b0[p + 500 * j]), x1 = vf_unpack (b1[p + 500 * j]);
-    bool z = (zero_mask >> j) & 1u;
-    v[j] = make_float2 (z ? 0.0f : x0, z ? 0.0f : x1);
-  }
-  vf_dft25_cols (v);
-  /* external twiddle w_N^(p k), k = 5 c + d:  (w^5)^c * w^d */
+  const uint32_t z = ~((((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) | 0x7F7F7F7Fu);   /* 0x80 where the byte is 0 */
+  return w | z;
+}
+
+/* Second half of a radix-25 pass: rows, twiddle by w^(5c+d) = q^c w^d
+ * (w, q = w^5 from tables rounded once from double), store X[5c+d] to
+ * o[(5c+d) * stride].  Products are formed at depth <= 3 multiplications. */
+VF_HD void vf_dft25_rows_store (float2 (&v)[25], float2 w1, float2 q1, float2 *o, int stride)
+{
   float2 w[5], q[5];
-  w[1] = tb.tw1[p];
-  w[2] = vf_cmul (w[1], w[1]);
-  w[3] = vf_cmul (w[2], w[1]);
+  w[1] = w1;
+  w[2] = vf_cmul (w1, w1);
+  w[3] = vf_cmul (w[2], w1);
   w[4] = vf_cmul (w[2], w[2]);
-  q[1] = tb.tw5[p];
-  q[2] = vf_cmul (q[1], q[1]);
-  q[3] = vf_cmul (q[2], q[1]);
+  q[1] = q1;
+  q[2] = vf_cmul (q1, q1);
+  q[3] = vf_cmul (q[2], q1);
   q[4] = vf_cmul (q[2], q[2]);
-  float2 *o = W + 25 * p;
   vf_dft25_row (v, 0);
   o[0] = v[0];
 #pragma unroll
-  for (int c = 1; c < 5; ++c) o[5 * c] = vf_cmul (v[c], q[c]);
+  for (int c = 1; c < 5; ++c) o[5 * c * stride] = vf_cmul (v[c], q[c]);
 #pragma unroll
   for (int d = 1; d < 5; ++d) {
     VF_SCHED_FENCE ();
     vf_dft25_row (v, d);
-    o[d] = vf_cmul (v[5 * d], w[d]);
+    o[d * stride] = vf_cmul (v[5 * d], w[d]);
 #pragma unroll
-    for (int c = 1; c < 5; ++c) o[5 * c + d] = vf_cmul (v[c + 5 * d], vf_cmul (q[c], w[d]));
+    for (int c = 1; c < 5; ++c) o[(5 * c + d) * stride] = vf_cmul (v[c + 5 * d], vf_cmul (q[c], w[d]));
   }
 }
 
-/* pass B, split at the barrier the in-place update needs */
-VF_HD void vf_pass_b_load (int i, const float2 *W, float2 (&v)[25])
-{
-#pragma unroll
-  for (int j = 0; j < 25; ++j) v[j] = W[i + 500 * j];
-}
+/* Twiddle tables (built on the host in double, rounded to float):
+ *   tw1[p] = w_12500^p, tw5[p] = w_12500^(5 p)      p  < 500   (pass 1)
+ *   u1[p'] = w_500^p',  u5[p'] = w_500^(5 p')       p' < 20    (pass 2)      */
+struct vf_fft_tables {
+  const float2 *tw1, *tw5, *u1, *u5;
+};
 
-VF_HD void vf_pass_b_store (int i, float2 (&v)[25], const vf_fft_tables &tb, float2 *W)
+/* pass 1: butterfly p in [0,500).  b0/b1 point at (sanitised) sample 0 of
+ * this FFT block for pol 0 / pol 1; bit j of zero_mask drops input j. */
+template <bool MASKED>
+VF_HD void vf_pass1 (int p, const uint8_t *b0, const uint8_t *b1, uint32_t zero_mask,
+                     const vf_fft_tables &tb, float2 *W)
 {
+  float2 v[25];
+#pragma unroll
+  for (int j = 0; j < 25; ++j) {
+    if (MASKED && ((zero_mask >> j) & 1u)) v[j] = make_float2 (0.0f, 0.0f);
+    else v[j] = make_float2 (vf_unpack_s (b0[p + 500 * j]), vf_unpack_s (b1[p + 500 * j]));
+  }
   vf_dft25_cols (v);
-  const int p = i / 25, q = i - 25 * p;
-  float2 *o = W + q + 625 * p;
-#pragma unroll
-  for (int d = 0; d < 5; ++d) {
-    vf_dft25_row (v, d);
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-      const int k = 5 * c + d;
-      if (k) o[25 * k] = vf_cmul (v[c + 5 * d], tb.tw500[p * k]);
-      else o[0] = v[0];
-    }
-    VF_SCHED_FENCE ();
-  }
+  vf_dft25_rows_store (v, tb.tw1[p], tb.tw5[p], W + p, VF_WS);
 }
 
-/* pass C */
-VF_HD void vf_pass_c_load (int q, const float2 *W, float2 (&v)[20])
+/* pass 2: butterfly b in [0,500): block k1 = b / 20, offset p' = b % 20; in place */
+VF_HD void vf_pass2 (int b, const vf_fft_tables &tb, float2 *W)
 {
+  const int k1 = b / 20, pp = b - 20 * k1;
+  float2 *o = W + VF_WS * k1 + pp;
+  float2 v[25];
 #pragma unroll
-  for (int j = 0; j < 20; ++j) v[j] = W[q + 625 * j];
+  for (int j = 0; j < 25; ++j) v[j] = o[20 * j];
+  vf_dft25_cols (v);
+  vf_dft25_rows_store (v, tb.u1[pp], tb.u5[pp], o, 20);
 }
 
-/* stores Z[q + 625 k] for the indices detection reads: [lo, hi] */
-VF_HD void vf_pass_c_store (int q, float2 (&v)[20], float2 *W, int lo, int hi)
+/* pass 3: butterfly m in [0,625): k1 = m % 25, k2 = m / 25; in place.  Only
+ * outputs k = k1 + 25 k2 + 625 k3 in [lo, hi] are stored. */
+VF_HD void vf_pass3 (int m, float2 *W, int lo, int hi)
 {
+  const int k2 = m / 25, k1 = m - 25 * k2;
+  float2 *o = W + VF_WS * k1 + 20 * k2;
+  float2 v[20];
+#pragma unroll
+  for (int j = 0; j < 20; ++j) v[j] = o[j];
   vf_dft20 (v);
+  const int kb = k1 + 25 * k2;
 #pragma unroll
   for (int d = 0; d < 5; ++d)
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int idx = q + 625 * (5 * c + d);
-      if (idx >= lo && idx <= hi) W[idx] = v[c + 4 * d];
+      const int k3 = 5 * c + d, k = kb + 625 * k3;
+      if (k >= lo && k <= hi) o[k3] = v[c + 4 * d];
     }
 }
 
-/* detection of output channel ch (FFT bin k = ch + chanmin) for both pols:
- * |X0[k]|^2 and |X1[k]|^2 from Z[k], Z[N-k]. */
-VF_HD float2 vf_detect (int k, const float2 *W)
+/* location of Z[k] after pass 3 */
+VF_HD int vf_zpos (int k)
 {
-  const float2 a = W[k], b = W[VF_NFFT - k];
+  const int k3 = k / 625, r = k - 625 * k3, k2 = r / 25, k1 = r - 25 * k2;
+  return VF_WS * k1 + 20 * k2 + k3;
+}
+
+/* detection of FFT bin k for both pols: |X0[k]|^2 and |X1[k]|^2 from Z[k], Z[N-k] */
+VF_HD float2 vf_detect_pair (float2 a, float2 b)
+{
   const float sr = a.x + b.x, si = a.y - b.y;     /* 2 X0 */
   const float dr = a.y + b.y, di = a.x - b.x;     /* 2 X1 = (dr, -di) */
   return make_float2 (0.25f * fmaf (sr, sr, si * si), 0.25f * fmaf (dr, dr, di * di));
+}
+
+VF_HD float2 vf_detect (int k, const float2 *W)
+{
+  return vf_detect_pair (W[vf_zpos (k)], W[vf_zpos (VF_NFFT - k)]);
 }
