@@ -64,7 +64,7 @@ typedef struct vf_config {
   int inject_frb;      /* 0      -i: allow vf_set_frb_injection                     */
   int gpu_id;          /* 0      -g                                                 */
   int n_antennas;      /* 1      antennas batched on this handle                    */
-  int k1_threads;      /* 0      0 = library default (320); 320, 512 or 640 (tuning) */
+  int k1_threads;      /* 0      0 = library default (640); 320, 512 or 640 (tuning) */
   int reserved[7];
 } vf_config;
 

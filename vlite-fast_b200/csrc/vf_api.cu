@@ -68,7 +68,7 @@ struct vf_handle {
   cudaEvent_t ev_k2_last;     /* completion of the most recent K2 */
   int have_k2_last;
   float2 *bp_raw, *bp_kur;    /* [n_ant][4096] (pol0, pol1) */
-  float2 *tw;                 /* tw1 | tw5 | u1 | u5 */
+  float2 *tw;                 /* tw1 | tw5 | tw500 */
   float *wtab;                /* [26] */
   float *pw, *kur, *dag, *pw_fb, *kur_fb, *dag_fb;
   unsigned int *histo;
@@ -83,7 +83,7 @@ struct vf_handle {
   /* co-add */
   vf_nccl_comm comm; int nranks, rank;
   float *coadd_sum; uint8_t *coadd_out;
-  int debug_sync;
+  int debug_sync, serial;
   char err[512];
 };
 
@@ -236,6 +236,9 @@ int vf_create (const vf_config *cfg, vf_handle **out)
   h->tile_elems = (size_t) h->T * VF_NCHANOUT;
   h->frb_nfft_since = -1;
   { const char *e = getenv ("VF_DEBUG_SYNC"); h->debug_sync = e && *e == '1'; }
+  /* VF_SERIAL=1: no overlap between segments, so that the per-kernel event times of
+   * vf_last_elapsed_ms are pure execution times (profiling aid) */
+  { const char *e = getenv ("VF_SERIAL"); h->serial = e && *e == '1'; }
 
   CK (cudaSetDevice (cfg->gpu_id));
   cudaDeviceProp prop;
@@ -258,21 +261,22 @@ int vf_create (const vf_config *cfg, vf_handle **out)
     CK (cudaMemset (h->bp_kur, 0, na * VF_NCHANOUT * sizeof (float2)));
   }
 
-  /* FFT twiddles in double, rounded once to float: w_12500^p, w_12500^(5p) (p < 500), w_500^p', w_500^(5p') (p' < 20) */
+  /* FFT twiddles in double, rounded once to float: w_12500^p, w_12500^(5p), w_500^p (p < 500) */
   {
-    std::vector<float2> tw (1040);
+    std::vector<float2> tw (1500);
     for (int p = 0; p < 500; ++p) {
       const double a1 = -2.0 * M_PI * p / 12500.0, a5 = -2.0 * M_PI * 5 * p / 12500.0;
       tw[p] = make_float2 ((float) cos (a1), (float) sin (a1));
       tw[500 + p] = make_float2 ((float) cos (a5), (float) sin (a5));
+      tw[1000 + p] = make_float2 (1.f, 0.f);
     }
-    for (int p = 0; p < 20; ++p) {
-      const double a1 = -2.0 * M_PI * p / 500.0, a5 = -2.0 * M_PI * 5 * p / 500.0;
-      tw[1000 + p] = make_float2 ((float) cos (a1), (float) sin (a1));
-      tw[1020 + p] = make_float2 ((float) cos (a5), (float) sin (a5));
-    }
-    CK (cudaMalloc ((void **) &h->tw, 1040 * sizeof (float2)));
-    CK (cudaMemcpy (h->tw, tw.data (), 1040 * sizeof (float2), cudaMemcpyHostToDevice));
+    for (int k = 1; k < 25; ++k)                 /* tw500[(k - 1) * 20 + p'] = w_500^(p' k) */
+      for (int pp = 0; pp < 20; ++pp) {
+        const double a = -2.0 * M_PI * (pp * k) / 500.0;
+        tw[1000 + (k - 1) * 20 + pp] = make_float2 ((float) cos (a), (float) sin (a));
+      }
+    CK (cudaMalloc ((void **) &h->tw, 1500 * sizeof (float2)));
+    CK (cudaMemcpy (h->tw, tw.data (), 1500 * sizeof (float2), cudaMemcpyHostToDevice));
   }
   /* weight of an FFT block with k kept sub-blocks: k sequential float adds of
    * float(NKURTO)/NFFT (atomicAdd, src/pb_kernels.cu:292) */
@@ -344,7 +348,7 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
   k1.pw = h->pw; k1.kur = h->kur; k1.dag = h->dag;
   k1.pw_fb = h->pw_fb; k1.kur_fb = h->kur_fb; k1.dag_fb = h->dag_fb;
   k1.histo = h->histo;
-  k1.tb.tw1 = h->tw; k1.tb.tw5 = h->tw + 500; k1.tb.u1 = h->tw + 1000; k1.tb.u5 = h->tw + 1020;
+  k1.tb.tw1 = h->tw; k1.tb.tw5 = h->tw + 500; k1.tb.tw500 = h->tw + 1000;
   memcpy (k1.dagc, h->dagc, sizeof (k1.dagc));
   memcpy (k1.dagc_fb, h->dagc_fb, sizeof (k1.dagc_fb));
   k1.wtab = h->wtab;
@@ -356,7 +360,8 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
   if (h->histo) CK (cudaMemsetAsync (h->histo, 0, (size_t) n_ant * 512 * sizeof (unsigned int), s->st));
   const int n_items = n_ant * h->T;
   const int grid = n_items < h->nsm ? n_items : h->nsm;
-  const int threads = c.k1_threads ? c.k1_threads : 320;
+  const int threads = c.k1_threads ? c.k1_threads : 640;
+  if (h->serial && h->have_k2_last) CK (cudaStreamWaitEvent (s->st, h->ev_k2_last, 0));
   if (timed >= 0) CK (cudaEventRecord (h->ev_ka[timed], s->st));
   CK (vf_launch_k1 (k1, grid, threads, s->st));
   if (h->debug_sync) CK (cudaStreamSynchronize (s->st));      /* VF_DEBUG_SYNC=1: attribute faults to a kernel */

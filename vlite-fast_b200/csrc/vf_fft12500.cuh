@@ -53,46 +53,86 @@
 #define VF_WS        501     /* padded block stride of W */
 #define VF_WLEN      (25 * VF_WS)
 
-/* v *= (wr + i wi), compile-time constant */
-#define VF_CMULC(v, wr, wi) do { float _x = (v).x, _y = (v).y; \
-  (v).x = fmaf (_x, (wr), -(_y * (wi))); (v).y = fmaf (_x, (wi), _y * (wr)); } while (0)
+/* ---- packed fp32 arithmetic ---------------------------------------------- *
+ * sm_100 has two-wide fp32 instructions (PTX add/mul/fma .f32x2, SASS FADD2 /
+ * FMUL2 / FFMA2) whose operands take a register pair with an optional swap
+ * (LO_HI), per-lane negation, or a broadcast scalar.  A complex number is such
+ * a pair, so one instruction updates re and im together and the +-i rotations
+ * and complex multiplies of the butterflies need no data movement: the FFT
+ * issues about half the instructions of the scalar form.  Each lane is an
+ * independent IEEE operation, so the results are bit-identical to the scalar
+ * expressions of the host fallback (which the CPU emulation test runs). */
+#if defined(__CUDA_ARCH__)
+VF_HD float2 vf_add2 (float2 a, float2 b)
+{
+  float2 r;
+  asm ("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+       : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+VF_HD float2 vf_mul2 (float2 a, float2 b)
+{
+  float2 r;
+  asm ("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+       : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+VF_HD float2 vf_fma2 (float2 a, float2 b, float2 c)
+{
+  float2 r;
+  asm ("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+       : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+#else
+VF_HD float2 vf_add2 (float2 a, float2 b) { return make_float2 (a.x + b.x, a.y + b.y); }
+VF_HD float2 vf_mul2 (float2 a, float2 b) { return make_float2 (a.x * b.x, a.y * b.y); }
+VF_HD float2 vf_fma2 (float2 a, float2 b, float2 c) { return make_float2 (fmaf (a.x, b.x, c.x), fmaf (a.y, b.y, c.y)); }
+#endif
+VF_HD float2 vf_bc (float s) { return make_float2 (s, s); }
+VF_HD float2 vf_sub2 (float2 a, float2 b) { return vf_add2 (a, make_float2 (-b.x, -b.y)); }
+/* a + (-i) u  and  a + i u */
+VF_HD float2 vf_add_mi (float2 a, float2 u) { return vf_add2 (a, make_float2 (u.y, -u.x)); }
+VF_HD float2 vf_add_pi (float2 a, float2 u) { return vf_add2 (a, make_float2 (-u.y, u.x)); }
 
-#include "vf_fft_consts.h"
-
+/* a b = (a.x b.x - a.y b.y, a.x b.y + a.y b.x): two packed instructions */
 VF_HD float2 vf_cmul (float2 a, float2 b)
 {
-  return make_float2 (fmaf (a.x, b.x, -(a.y * b.y)), fmaf (a.x, b.y, a.y * b.x));
+  return vf_fma2 (vf_bc (a.x), b, vf_mul2 (vf_bc (a.y), make_float2 (-b.y, b.x)));
 }
+
+/* v *= (wr + i wi), compile-time constant */
+#define VF_CMULC(v, wr, wi) do { (v) = vf_cmul ((v), make_float2 ((wr), (wi))); } while (0)
+
+#include "vf_fft_consts.h"
 
 /* forward radix-5 butterfly, in place: a_k <- sum_j a_j exp(-2 pi i j k / 5) */
 VF_HD void vf_r5 (float2 &a0, float2 &a1, float2 &a2, float2 &a3, float2 &a4)
 {
   const float c1 = 0.30901699437494745f, c2 = -0.80901699437494745f;
   const float s1 = 0.95105651629515353f, s2 = 0.58778525229247314f;
-  float2 t1 = make_float2 (a1.x + a4.x, a1.y + a4.y);
-  float2 t2 = make_float2 (a2.x + a3.x, a2.y + a3.y);
-  float2 t3 = make_float2 (a1.x - a4.x, a1.y - a4.y);
-  float2 t4 = make_float2 (a2.x - a3.x, a2.y - a3.y);
-  float2 m1 = make_float2 (fmaf (c2, t2.x, fmaf (c1, t1.x, a0.x)), fmaf (c2, t2.y, fmaf (c1, t1.y, a0.y)));
-  float2 m2 = make_float2 (fmaf (c1, t2.x, fmaf (c2, t1.x, a0.x)), fmaf (c1, t2.y, fmaf (c2, t1.y, a0.y)));
-  float2 u1 = make_float2 (fmaf (s2, t4.x, s1 * t3.x), fmaf (s2, t4.y, s1 * t3.y));
-  float2 u2 = make_float2 (fmaf (-s1, t4.x, s2 * t3.x), fmaf (-s1, t4.y, s2 * t3.y));
-  a0 = make_float2 (a0.x + t1.x + t2.x, a0.y + t1.y + t2.y);
-  a1 = make_float2 (m1.x + u1.y, m1.y - u1.x);
-  a4 = make_float2 (m1.x - u1.y, m1.y + u1.x);
-  a2 = make_float2 (m2.x + u2.y, m2.y - u2.x);
-  a3 = make_float2 (m2.x - u2.y, m2.y + u2.x);
+  const float2 t1 = vf_add2 (a1, a4), t2 = vf_add2 (a2, a3);
+  const float2 t3 = vf_sub2 (a1, a4), t4 = vf_sub2 (a2, a3);
+  const float2 m1 = vf_fma2 (vf_bc (c2), t2, vf_fma2 (vf_bc (c1), t1, a0));
+  const float2 m2 = vf_fma2 (vf_bc (c1), t2, vf_fma2 (vf_bc (c2), t1, a0));
+  const float2 u1 = vf_fma2 (vf_bc (s2), t4, vf_mul2 (vf_bc (s1), t3));
+  const float2 u2 = vf_fma2 (vf_bc (-s1), t4, vf_mul2 (vf_bc (s2), t3));
+  a0 = vf_add2 (vf_add2 (a0, t1), t2);
+  a1 = vf_add_mi (m1, u1);
+  a4 = vf_add_pi (m1, u1);
+  a2 = vf_add_mi (m2, u2);
+  a3 = vf_add_pi (m2, u2);
 }
 
 /* forward radix-4 butterfly, in place */
 VF_HD void vf_r4 (float2 &a0, float2 &a1, float2 &a2, float2 &a3)
 {
-  float2 e0 = make_float2 (a0.x + a2.x, a0.y + a2.y), e1 = make_float2 (a0.x - a2.x, a0.y - a2.y);
-  float2 o0 = make_float2 (a1.x + a3.x, a1.y + a3.y), o1 = make_float2 (a1.x - a3.x, a1.y - a3.y);
-  a0 = make_float2 (e0.x + o0.x, e0.y + o0.y);
-  a2 = make_float2 (e0.x - o0.x, e0.y - o0.y);
-  a1 = make_float2 (e1.x + o1.y, e1.y - o1.x);
-  a3 = make_float2 (e1.x - o1.y, e1.y + o1.x);
+  const float2 e0 = vf_add2 (a0, a2), e1 = vf_sub2 (a0, a2);
+  const float2 o0 = vf_add2 (a1, a3), o1 = vf_sub2 (a1, a3);
+  a0 = vf_add2 (e0, o0);
+  a2 = vf_sub2 (e0, o0);
+  a1 = vf_add_mi (e1, o1);
+  a3 = vf_add_pi (e1, o1);
 }
 
 /* 25-point DFT of v[j], j = a + 5 b, in two halves so that callers can
@@ -130,6 +170,17 @@ VF_HD float vf_unpack_s (unsigned u)
   return fmaf (v, 0.0078125f, -65537.0f);
 }
 
+/* both polarisations of one sample in one packed FMA */
+VF_HD float2 vf_unpack2_s (unsigned u0, unsigned u1)
+{
+#if defined(__CUDA_ARCH__)
+  const float2 v = make_float2 (__uint_as_float (0x4B000000u | u0), __uint_as_float (0x4B000000u | u1));
+#else
+  const float2 v = make_float2 (8388608.0f + (float) u0, 8388608.0f + (float) u1);
+#endif
+  return vf_fma2 (v, vf_bc (0.0078125f), vf_bc (-65537.0f));
+}
+
 /* 0 -> 128 in every byte of a word */
 VF_HD uint32_t vf_sanitise_word (uint32_t w)
 {
@@ -165,11 +216,28 @@ VF_HD void vf_dft25_rows_store (float2 (&v)[25], float2 w1, float2 q1, float2 *o
   }
 }
 
+/* Same with one table look-up per output: tw[(k - 1) * 20 + pk] = w_500^(pk k), laid out so that the
+ * threads of a warp (consecutive pk) read consecutive entries */
+VF_HD void vf_dft25_rows_store_tab (float2 (&v)[25], const float2 *tw, int pk, float2 *o, int stride)
+{
+#pragma unroll
+  for (int d = 0; d < 5; ++d) {
+    vf_dft25_row (v, d);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      const int k = 5 * c + d;
+      if (k) o[k * stride] = vf_cmul (v[c + 5 * d], tw[(k - 1) * 20 + pk]);
+      else o[0] = v[0];
+    }
+    VF_SCHED_FENCE ();
+  }
+}
+
 /* Twiddle tables (built on the host in double, rounded to float):
- *   tw1[p] = w_12500^p, tw5[p] = w_12500^(5 p)      p  < 500   (pass 1)
- *   u1[p'] = w_500^p',  u5[p'] = w_500^(5 p')       p' < 20    (pass 2)      */
+ *   tw1[p] = w_12500^p, tw5[p] = w_12500^(5 p)      p < 500   (pass 1: 12000 distinct twiddles, formed as products)
+ *   tw500[(k2 - 1) * 20 + p'] = w_500^(p' k2)       p' < 20, 1 <= k2 < 25   (pass 2)                              */
 struct vf_fft_tables {
-  const float2 *tw1, *tw5, *u1, *u5;
+  const float2 *tw1, *tw5, *tw500;
 };
 
 /* pass 1: butterfly p in [0,500).  b0/b1 point at (sanitised) sample 0 of
@@ -182,7 +250,7 @@ VF_HD void vf_pass1 (int p, const uint8_t *b0, const uint8_t *b1, uint32_t zero_
 #pragma unroll
   for (int j = 0; j < 25; ++j) {
     if (MASKED && ((zero_mask >> j) & 1u)) v[j] = make_float2 (0.0f, 0.0f);
-    else v[j] = make_float2 (vf_unpack_s (b0[p + 500 * j]), vf_unpack_s (b1[p + 500 * j]));
+    else v[j] = vf_unpack2_s (b0[p + 500 * j], b1[p + 500 * j]);
   }
   vf_dft25_cols (v);
   vf_dft25_rows_store (v, tb.tw1[p], tb.tw5[p], W + p, VF_WS);
@@ -197,7 +265,7 @@ VF_HD void vf_pass2 (int b, const vf_fft_tables &tb, float2 *W)
 #pragma unroll
   for (int j = 0; j < 25; ++j) v[j] = o[20 * j];
   vf_dft25_cols (v);
-  vf_dft25_rows_store (v, tb.u1[pp], tb.u5[pp], o, 20);
+  vf_dft25_rows_store_tab (v, tb.tw500, pp, o, 20);
 }
 
 /* pass 3: butterfly m in [0,625): k1 = m % 25, k2 = m / 25; in place.  Only
@@ -230,9 +298,10 @@ VF_HD int vf_zpos (int k)
 /* detection of FFT bin k for both pols: |X0[k]|^2 and |X1[k]|^2 from Z[k], Z[N-k] */
 VF_HD float2 vf_detect_pair (float2 a, float2 b)
 {
-  const float sr = a.x + b.x, si = a.y - b.y;     /* 2 X0 */
-  const float dr = a.y + b.y, di = a.x - b.x;     /* 2 X1 = (dr, -di) */
-  return make_float2 (0.25f * fmaf (sr, sr, si * si), 0.25f * fmaf (dr, dr, di * di));
+  const float2 s = vf_add2 (a, make_float2 (b.x, -b.y));      /* 2 X0 = (a.x + b.x, a.y - b.y)             */
+  const float2 d = vf_add2 (a, make_float2 (-b.x, b.y));      /* (a.x - b.x, a.y + b.y): 2 X1 = (d.y, -d.x) */
+  /* (s.x^2 + s.y^2, d.y^2 + d.x^2) / 4 */
+  return vf_mul2 (vf_bc (0.25f), vf_fma2 (make_float2 (s.x, d.y), make_float2 (s.x, d.y), vf_mul2 (make_float2 (s.y, d.x), make_float2 (s.y, d.x))));
 }
 
 VF_HD float2 vf_detect (int k, const float2 *W)

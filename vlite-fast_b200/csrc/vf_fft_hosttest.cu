@@ -23,18 +23,18 @@ int main (int argc, char **argv)
     w = vf_sanitise_word (w);
     memcpy (&b[i], &w, 4);
   }
-  std::vector<float2> tw1 (500), tw5 (500), u1 (20), u5 (20), W (VF_WLEN, make_float2 (0.f, 0.f));
+  std::vector<float2> tw1 (500), tw5 (500), tw500 (500), W (VF_WLEN, make_float2 (0.f, 0.f));
   for (int p = 0; p < 500; ++p) {
     double a1 = -2.0 * M_PI * p / 12500.0, a5 = -2.0 * M_PI * 5 * p / 12500.0;
     tw1[p] = make_float2 ((float) cos (a1), (float) sin (a1));
     tw5[p] = make_float2 ((float) cos (a5), (float) sin (a5));
   }
-  for (int p = 0; p < 20; ++p) {
-    double a1 = -2.0 * M_PI * p / 500.0, a5 = -2.0 * M_PI * 5 * p / 500.0;
-    u1[p] = make_float2 ((float) cos (a1), (float) sin (a1));
-    u5[p] = make_float2 ((float) cos (a5), (float) sin (a5));
-  }
-  vf_fft_tables tb = { tw1.data (), tw5.data (), u1.data (), u5.data () };
+  for (int k = 1; k < 25; ++k)
+    for (int p = 0; p < 20; ++p) {
+      double a = -2.0 * M_PI * (p * k) / 500.0;
+      tw500[(k - 1) * 20 + p] = make_float2 ((float) cos (a), (float) sin (a));
+    }
+  vf_fft_tables tb = { tw1.data (), tw5.data (), tw500.data () };
   for (int p = 0; p < VF_NA; ++p) {
     if (mask) vf_pass1<true> (p, b.data (), b.data () + 12500, mask, tb, W.data ());
     else vf_pass1<false> (p, b.data (), b.data () + 12500, 0, tb, W.data ());
