@@ -185,7 +185,8 @@ def main():
     pkg = ge.load_package()
     n_ant = args.antennas
     p = pkg.Pipeline(ffts_per_seg=T, nbit=args.nbit, npol=args.npol, rfi_mode=args.rfi_mode, gpu_id=local,
-                     n_antennas=n_ant, keep_power=1 if world > 1 else 0, k1_threads=args.k1_threads)
+                     n_antennas=n_ant, keep_power=1 if world > 1 else 0, k1_threads=args.k1_threads,
+                     power_segments=2 * SEG_PER_SEC if world > 1 else 0)
     out_bytes = p.out_bytes
 
     # ---- inputs: one antenna-second per antenna, pinned on the host and resident on the device
@@ -217,9 +218,8 @@ def main():
         if world == 1:
             p.process_device(n_ant, SEG_PER_SEC, d_in.data_ptr(), d_main.data_ptr(), d_raw.data_ptr() if d_raw is not None else None)
         else:
-            for s in range(SEG_PER_SEC):
-                p.process_device(n_ant, 1, d_in[s].data_ptr(), d_main[s].data_ptr(), d_raw[s].data_ptr() if d_raw is not None else None)
-                p.coadd_segment(0, world * n_ant, want=False)
+            p.process_device(n_ant, SEG_PER_SEC, d_in.data_ptr(), d_main.data_ptr(), d_raw.data_ptr() if d_raw is not None else None)
+            p.coadd_batch(0, world * n_ant, SEG_PER_SEC, want=False, wait=False)      # one reduce per second
 
     # ---- device-resident timing -------------------------------------------------
     for _ in range(args.warmup):
@@ -337,11 +337,11 @@ def main():
                                "default channelisation, kurtosis excision on",
                    "antennas_per_gpu": n_ant, "nbit": args.nbit, "npol": args.npol, "rfi_mode": args.rfi_mode,
                    "l2": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2; no flush" % (n_ant * 2 * NSAMP * SEG_PER_SEC / 1e6),
-                   "generator": GEN, "coadd": "NCCL reduce of f32 tiles per segment" if world > 1 else "none",
+                   "generator": GEN, "coadd": "one NCCL reduce of the f32 tiles of the 10 segments per step" if world > 1 else "none",
                    "timing": "CUDA events on the library's stream (fork/join over its 2 slot streams)" if world == 1
                              else "wall clock between barrier+synchronize, max over ranks"},
         "clocks": clocks, "e2e": e2e,
-        "gpu_launches": int(args.steps * SEG_PER_SEC * 2 * (1 if world == 1 else 1) + (args.steps * SEG_PER_SEC * (n_ant + 1) if world > 1 else 0)),
+        "gpu_launches": int(args.steps * SEG_PER_SEC * 2 + (args.steps * SEG_PER_SEC * n_ant if world > 1 else 0)),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "legacy_cuda": legacy,
         "wall_ms_per_step": 1e3 * wall / args.steps,
     }

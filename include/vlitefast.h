@@ -65,7 +65,9 @@ typedef struct vf_config {
   int gpu_id;          /* 0      -g                                                 */
   int n_antennas;      /* 1      antennas batched on this handle                    */
   int k1_threads;      /* 0      0 = library default (640); 320, 512 or 640 (tuning) */
-  int reserved[7];
+  int power_segments;  /* 0      f32 tiles kept for this many consecutive segments (0 = 1): lets
+                                 vf_coadd_batch reduce a whole second in one collective       */
+  int reserved[6];
 } vf_config;
 
 typedef struct vf_handle vf_handle;
@@ -179,6 +181,11 @@ int vf_coadd_init (vf_handle *h, int nranks, int rank, const void *nccl_unique_i
 int vf_coadd_unique_id (void *out128);               /* ncclGetUniqueId */
 int vf_coadd_segment (vf_handle *h, int root, int total_antennas, uint8_t *fb_coadd /*host, root only*/,
                       float *sum_f32 /*host, optional, root only*/);
+/* The same for the last n_seg segments (n_seg <= power_segments) in ONE reduce:
+ * the exchange is 2 MiB per antenna-segment, i.e. latency bound, so a second
+ * of segments is reduced at once.  Outputs are [n_seg][...] in segment order.
+ * wait == 0: returns once enqueued on the library's stream (vf_sync waits). */
+int vf_coadd_batch (vf_handle *h, int root, int total_antennas, int n_seg, uint8_t *fb_coadd, float *sum_f32, int wait);
 
 #ifdef __cplusplus
 }

@@ -223,3 +223,26 @@ def test_ragged_segment_lengths(pkg, orc, T, nbit, npol):
         check_bytes(raw, oraw, nbit, "raw")
     assert np.array_equal(p.get_mask(), o.mask())
     p.close()
+
+
+def test_coadd_batch_of_segments(pkg, orc):
+    """tiles of 3 consecutive segments kept and co-added in one call"""
+    T, n, nseg = 16, 2, 3
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=1, n_antennas=n, keep_power=1, power_segments=4) as p:
+        p.coadd_init()
+        oracles = [orc.OracleChain(T, 8, 1, 1) for _ in range(n)]
+        want = []
+        for s in range(nseg + 2):                  # two extra segments first: the tile ring wraps
+            ins = [make_input(pkg, T, seed=80, antenna=a, sample0=s * T * 12500, **RFI) for a in range(n)]
+            p.process_batch([i[0] for i in ins], [i[1] for i in ins])
+            tiles = []
+            for a in range(n):
+                oracles[a].process_segment(*ins[a])
+                tiles.append(oracles[a].ave_trimmed("main"))
+            want.append(tiles[0] + tiles[1])
+        fb, sm = p.coadd_batch(0, n, nseg)
+        for i in range(nseg):
+            assert np.abs(sm[i] - want[2 + i]).max() < 5e-4, i
+        assert fb.shape == (nseg, T // 8 * 4096)
+        with pytest.raises(pkg.VfError):
+            p.coadd_batch(0, n, 5)

@@ -28,7 +28,7 @@ class VfConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "abi_version", "nfft", "nscrunch", "ffts_per_seg", "nkurto", "chanmin", "chanmax", "nbit",
         "npol", "rfi_mode", "do_histo", "keep_stats", "keep_power", "inject_frb", "gpu_id",
-        "n_antennas", "k1_threads")] + [("reserved", C.c_int * 7)]
+        "n_antennas", "k1_threads", "power_segments")] + [("reserved", C.c_int * 6)]
 
 
 def _load(name):
@@ -81,6 +81,7 @@ def lib():
     L.vf_coadd_init.argtypes = [vp, i, i, vp]
     L.vf_coadd_unique_id.argtypes = [vp]
     L.vf_coadd_segment.argtypes = [vp, i, i, vp, vp]
+    L.vf_coadd_batch.argtypes = [vp, i, i, i, vp, vp, i]
     _lib = L
     return L
 
@@ -302,6 +303,13 @@ class Pipeline:
     def coadd_init(self, nranks=1, rank=0, unique_id=None):
         buf = C.create_string_buffer(unique_id, 128) if unique_id else None
         self._ck(self.L.vf_coadd_init(self.h, nranks, rank, buf))
+
+    def coadd_batch(self, root, total_antennas, n_seg, want=True, wait=True):
+        n = self.cfg.npol * self.ntime * NCHANOUT
+        fb = np.empty((n_seg, n * self.cfg.nbit // 8), np.uint8) if want else None
+        sm = np.empty((n_seg, self.cfg.npol, self.ntime, NCHANOUT), np.float32) if want else None
+        self._ck(self.L.vf_coadd_batch(self.h, root, total_antennas, n_seg, _ptr(fb), _ptr(sm), 1 if (wait or want) else 0))
+        return fb, sm
 
     def coadd_segment(self, root, total_antennas, want=True):
         n = self.cfg.npol * self.ntime * NCHANOUT

@@ -72,7 +72,9 @@ struct vf_handle {
   float *wtab;                /* [26] */
   float *pw, *kur, *dag, *pw_fb, *kur_fb, *dag_fb;
   unsigned int *histo;
-  float *ave_main, *ave_raw;  /* [n_ant][npol][T/8][4096] */
+  float *ave_main, *ave_raw;  /* [ave_nseg][n_ant][npol][T/8][4096] */
+  int ave_nseg;               /* tiles kept (ring over consecutive segments) */
+  long seg_counter;           /* segments enqueued so far */
   float *frb_delays;
   int frb_nfft_since; float frb_width, frb_amp; float frb_dm;
   double dagc[5], dagc_fb[5];
@@ -82,6 +84,8 @@ struct vf_handle {
   int n_timed, timed_valid;
   /* co-add */
   vf_nccl_comm comm; int nranks, rank;
+  struct { cudaEvent_t ev; long lo, hi; int pending; } coadd_batch[2];   /* the last two co-add batches */
+  int coadd_next;
   float *coadd_sum; uint8_t *coadd_out;
   int debug_sync, serial;
   char err[512];
@@ -194,6 +198,7 @@ int vf_destroy (vf_handle *h)
   if (h->ev_t0) cudaEventDestroy (h->ev_t0);
   if (h->ev_t1) cudaEventDestroy (h->ev_t1);
   if (h->ev_k2_last) cudaEventDestroy (h->ev_k2_last);
+  for (int b = 0; b < 2; ++b) if (h->coadd_batch[b].ev) cudaEventDestroy (h->coadd_batch[b].ev);
   for (int i = 0; i < VF_MAX_TIMED_SEG; ++i) {
     if (h->ev_ka[i]) cudaEventDestroy (h->ev_ka[i]);
     if (h->ev_kb[i]) cudaEventDestroy (h->ev_kb[i]);
@@ -302,8 +307,9 @@ int vf_create (const vf_config *cfg, vf_handle **out)
     h->dag_fb = h->pw_fb + na * 4 * h->T;
   }
   if (cfg->do_histo) CK (cudaMalloc ((void **) &h->histo, na * 512 * sizeof (unsigned int)));
+  h->ave_nseg = cfg->power_segments > 0 ? cfg->power_segments : 1;
   if (cfg->keep_power) {
-    const size_t n = na * cfg->npol * h->ntime * VF_NCHANOUT;
+    const size_t n = (size_t) h->ave_nseg * na * cfg->npol * h->ntime * VF_NCHANOUT;
     CK (cudaMalloc ((void **) &h->ave_main, n * sizeof (float)));
     CK (cudaMemset (h->ave_main, 0, n * sizeof (float)));
     if (cfg->rfi_mode == 2) {
@@ -369,6 +375,14 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
 
   /* the bandpass makes K2 launches sequential in segment order */
   if (h->have_k2_last) CK (cudaStreamWaitEvent (s->st, h->ev_k2_last, 0));
+  /* this segment overwrites the tile of segment (seg_counter - ave_nseg): wait for a co-add that still reads it */
+  for (int b = 0; b < 2; ++b) {
+    const long victim = h->seg_counter - h->ave_nseg;
+    if (h->coadd_batch[b].pending && victim >= h->coadd_batch[b].lo && victim < h->coadd_batch[b].hi) {
+      CK (cudaStreamWaitEvent (s->st, h->coadd_batch[b].ev, 0));
+      h->coadd_batch[b].pending = 0;
+    }
+  }
   vf_k2_params k2;
   memset (&k2, 0, sizeof (k2));
   k2.P_raw = s->P_raw; k2.P_kur = s->P_kur; k2.w = s->w; k2.mask = s->mask;
@@ -377,7 +391,14 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
   /* bp_scale = float(tsamp/tsmooth), src/process_baseband.cu:737-741 */
   k2.bp_scale = (float) (((double) VF_NFFT / 128000000 * VF_NSCRUNCH) / 1.0);
   k2.out_main = d_main; k2.out_raw = d_raw; k2.out_stride = h->out_bytes;
-  k2.ave_main = h->ave_main; k2.ave_raw = h->ave_raw;
+  {
+    /* tile slot of this segment in the ring of kept tiles (sized for the handle's n_antennas) */
+    const size_t tile_all = (size_t) h->n_ant * c.npol * h->ntime * VF_NCHANOUT;
+    const size_t off = (size_t) (h->seg_counter % h->ave_nseg) * tile_all;
+    k2.ave_main = h->ave_main ? h->ave_main + off : NULL;
+    k2.ave_raw = h->ave_raw ? h->ave_raw + off : NULL;
+    h->seg_counter++;
+  }
   CK (vf_launch_k2 (k2, s->st));
   if (h->debug_sync) CK (cudaStreamSynchronize (s->st));
   if (timed >= 0) CK (cudaEventRecord (h->ev_kc[timed], s->st));
@@ -670,7 +691,8 @@ int vf_get_power_f32 (vf_handle *h, int antenna, int which, float *out)
   rc = vf_sync (h);
   if (rc) return rc;
   const size_t n = (size_t) h->cfg.npol * h->ntime * VF_NCHANOUT;
-  CK (cudaMemcpy (out, src + (size_t) antenna * n, n * 4, cudaMemcpyDeviceToHost));
+  const size_t last = (size_t) ((h->seg_counter + h->ave_nseg - 1) % h->ave_nseg) * h->n_ant * n;
+  CK (cudaMemcpy (out, src + last + (size_t) antenna * n, n * 4, cudaMemcpyDeviceToHost));
   return VF_OK;
 }
 
@@ -812,8 +834,10 @@ int vf_coadd_init (vf_handle *h, int nranks, int rank, const void *nccl_unique_i
   CK (cudaSetDevice (h->cfg.gpu_id));
   const size_t n = (size_t) h->cfg.npol * h->ntime * VF_NCHANOUT;
   if (!h->coadd_sum) {
-    CK (cudaMalloc ((void **) &h->coadd_sum, n * sizeof (float)));
-    CK (cudaMalloc ((void **) &h->coadd_out, n * h->cfg.nbit / 8));
+    CK (cudaMalloc ((void **) &h->coadd_sum, n * h->ave_nseg * sizeof (float)));
+    CK (cudaMalloc ((void **) &h->coadd_out, n * h->ave_nseg * h->cfg.nbit / 8));
+    CK (cudaEventCreateWithFlags (&h->coadd_batch[0].ev, cudaEventDisableTiming));
+    CK (cudaEventCreateWithFlags (&h->coadd_batch[1].ev, cudaEventDisableTiming));
   }
   h->nranks = nranks; h->rank = rank;
   if (nranks > 1) {
@@ -828,35 +852,59 @@ int vf_coadd_init (vf_handle *h, int nranks, int rank, const void *nccl_unique_i
   return VF_OK;
 }
 
-int vf_coadd_segment (vf_handle *h, int root, int total_antennas, uint8_t *fb_coadd, float *sum_f32)
+int vf_coadd_batch (vf_handle *h, int root, int total_antennas, int n_seg, uint8_t *fb_coadd, float *sum_f32, int wait)
 {
-  if (!h || total_antennas < 1) return VF_ERR_ARG;
+  if (!h || total_antennas < 1 || n_seg < 1) return VF_ERR_ARG;
   if (!h->coadd_sum) return vf_fail (h, VF_ERR_STATE, "vf_coadd_init not called");
+  if (n_seg > h->ave_nseg || n_seg > h->seg_counter)
+    return vf_fail (h, VF_ERR_ARG, "n_seg %d exceeds the %d kept tile(s)", n_seg, h->ave_nseg);
   if (root < 0 || root >= (h->nranks ? h->nranks : 1)) return vf_fail (h, VF_ERR_ARG, "bad root");
   CK (cudaSetDevice (h->cfg.gpu_id));
-  const size_t n = (size_t) h->cfg.npol * h->ntime * VF_NCHANOUT;
+  const size_t n = (size_t) h->cfg.npol * h->ntime * VF_NCHANOUT;        /* one tile */
+  const size_t out1 = n * h->cfg.nbit / 8;
   cudaStream_t st = h->ctl;
   /* after every K2 that wrote the tiles */
   if (h->have_k2_last) CK (cudaStreamWaitEvent (st, h->ev_k2_last, 0));
-  CK (cudaMemcpyAsync (h->coadd_sum, h->ave_main, n * sizeof (float), cudaMemcpyDeviceToDevice, st));
-  for (int a = 1; a < h->n_ant; ++a)
-    CK (vf_launch_accum (h->coadd_sum, h->ave_main + (size_t) a * n, n, st));
+  /* local sum over this handle's antennas, segment by segment in time order */
+  for (int i = 0; i < n_seg; ++i) {
+    const long seg = h->seg_counter - n_seg + i;
+    const float *tiles = h->ave_main + (size_t) (seg % h->ave_nseg) * h->n_ant * n;
+    float *dst = h->coadd_sum + (size_t) i * n;
+    CK (cudaMemcpyAsync (dst, tiles, n * sizeof (float), cudaMemcpyDeviceToDevice, st));
+    for (int a = 1; a < h->n_ant; ++a)
+      CK (vf_launch_accum (dst, tiles + (size_t) a * n, n, st));
+  }
   if (h->nranks > 1) {
-    /* ncclFloat32 = 7, ncclSum = 0 (nccl.h) */
-    int e = g_nccl.Reduce (h->coadd_sum, h->coadd_sum, n, 7, 0, root, h->comm, st);
+    /* ncclFloat32 = 7, ncclSum = 0 (nccl.h); one collective for the whole batch */
+    int e = g_nccl.Reduce (h->coadd_sum, h->coadd_sum, n * n_seg, 7, 0, root, h->comm, st);
     if (e != 0) return vf_fail (h, VF_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString (e) : "?");
   }
   if (h->rank == root) {
-    vf_coadd_params cp;
-    cp.sum = h->coadd_sum; cp.cnt = NULL;
-    cp.scale = (float) (1.0 / sqrt ((double) total_antennas));
-    cp.ntime = h->ntime; cp.npol = h->cfg.npol; cp.nbit = h->cfg.nbit; cp.out = h->coadd_out;
-    CK (vf_launch_coadd (cp, st));
-    if (fb_coadd) CK (cudaMemcpyAsync (fb_coadd, h->coadd_out, n * h->cfg.nbit / 8, cudaMemcpyDeviceToHost, st));
-    if (sum_f32) CK (cudaMemcpyAsync (sum_f32, h->coadd_sum, n * sizeof (float), cudaMemcpyDeviceToHost, st));
+    for (int i = 0; i < n_seg; ++i) {
+      vf_coadd_params cp;
+      cp.sum = h->coadd_sum + (size_t) i * n; cp.cnt = NULL;
+      cp.scale = (float) (1.0 / sqrt ((double) total_antennas));
+      cp.ntime = h->ntime; cp.npol = h->cfg.npol; cp.nbit = h->cfg.nbit; cp.out = h->coadd_out + (size_t) i * out1;
+      CK (vf_launch_coadd (cp, st));
+    }
+    if (fb_coadd) CK (cudaMemcpyAsync (fb_coadd, h->coadd_out, out1 * n_seg, cudaMemcpyDeviceToHost, st));
+    if (sum_f32) CK (cudaMemcpyAsync (sum_f32, h->coadd_sum, n * n_seg * sizeof (float), cudaMemcpyDeviceToHost, st));
   }
-  CK (cudaStreamSynchronize (st));
+  /* later segments overwrite the tile ring: those that hit this batch's tiles wait for it */
+  {
+    const int b = h->coadd_next;
+    if (h->coadd_batch[b].pending) CK (cudaStreamWaitEvent (st, h->coadd_batch[b].ev, 0));   /* same stream: already ordered */
+    CK (cudaEventRecord (h->coadd_batch[b].ev, st));
+    h->coadd_batch[b].lo = h->seg_counter - n_seg; h->coadd_batch[b].hi = h->seg_counter; h->coadd_batch[b].pending = 1;
+    h->coadd_next ^= 1;
+  }
+  if (wait) CK (cudaStreamSynchronize (st));
   return VF_OK;
+}
+
+int vf_coadd_segment (vf_handle *h, int root, int total_antennas, uint8_t *fb_coadd, float *sum_f32)
+{
+  return vf_coadd_batch (h, root, total_antennas, 1, fb_coadd, sum_f32, 1);
 }
 
 } /* extern "C" */
