@@ -134,6 +134,9 @@ int vf_sync (vf_handle *h);
 /* elapsed device time between the start and end of the last vf_process_device
  * / vf_process_* call, from CUDA events on the library's stream (ms) */
 int vf_last_elapsed_ms (vf_handle *h, float *total_ms, float *k1_ms, float *k2_ms);
+/* profiling aid: serial != 0 stops consecutive segments from overlapping, which makes k1_ms / k2_ms
+ * above pure kernel execution times (with overlap they include waiting for SMs) */
+int vf_set_serial (vf_handle *h, int serial);
 
 /* pinned host memory helpers (cudaMallocHost, :578-579) */
 int vf_host_alloc (void **p, size_t bytes);

@@ -66,6 +66,7 @@ def lib():
     L.vf_submit_vdif_async.argtypes = [vp, i, i, vp, sz, C.c_uint32, u8p, u8p]
     L.vf_process_device.argtypes = [vp, i, i, vp, vp, vp]
     L.vf_sync.argtypes = [vp]
+    L.vf_set_serial.argtypes = [vp, i]
     fp = C.POINTER(C.c_float)
     L.vf_last_elapsed_ms.argtypes = [vp, fp, fp, fp]
     L.vf_host_alloc.argtypes = [C.POINTER(vp), sz]
@@ -236,6 +237,9 @@ class Pipeline:
     def process_device(self, n_ant, n_seg, d_in, d_main, d_raw=None):
         """device pointers (ints); asynchronous, see sync()."""
         self._ck(self.L.vf_process_device(self.h, n_ant, n_seg, d_in, d_main, d_raw))
+
+    def set_serial(self, serial):
+        self._ck(self.L.vf_set_serial(self.h, int(serial)))
 
     def sync(self):
         self._ck(self.L.vf_sync(self.h))

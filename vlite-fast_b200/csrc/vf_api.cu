@@ -603,6 +603,15 @@ int vf_process_device (vf_handle *h, int n_ant, int n_seg, const uint8_t *d_in,
   return vf_timing_end (h);
 }
 
+/* serial != 0: segments do not overlap (K1 of segment n+1 waits for K2 of segment n), so that the
+ * per-kernel times of vf_last_elapsed_ms are pure execution times.  Also set by VF_SERIAL=1. */
+int vf_set_serial (vf_handle *h, int serial)
+{
+  if (!h) return VF_ERR_ARG;
+  h->serial = serial != 0;
+  return VF_OK;
+}
+
 int vf_sync (vf_handle *h)
 {
   if (!h) return VF_ERR_ARG;

@@ -265,6 +265,7 @@ int main (int argc, char **argv)
     long seconds_done = 0, seg_counter = 0;
     int first = 1, aborted = 0;
     int pend_slot[2] = {0, 0};
+    int blocks_open = 0;
     vf_reset_bandpass (h, -1);    /* the reference keeps the bandpass across observations (:700-709); a new
                                      stream here is a new antenna-time, so start clean */
 
@@ -274,15 +275,15 @@ int main (int argc, char **argv)
       if (!blk) break;                                            /* end of data: primary exit, :1044-1051 */
       if (nbytes < SEC_BYTES) {
         logmsg ("INFO", "Incomplete final second (%lu bytes), dropped.\n", (unsigned long) nbytes);
-        vf_ring_block_read_close (ring);
-        continue;
+        blocks_open++;
+        break;
       }
       const vf_vdif_header *vh = (const vf_vdif_header *) blk;
       if (first) {
         if (vf_vdif_frame_number (vh) != 0 || vf_vdif_thread_id (vh) != 0) {     /* :843-849 */
           logmsg ("ERR", "Incoming data were not aligned!\n");
           exit_status = 1; aborted = 1;
-          vf_ring_block_read_close (ring);
+          blocks_open++;
           break;
         }
         if (write_fb) {                                           /* :852-998 */
@@ -293,7 +294,7 @@ int main (int argc, char **argv)
             if (cfg.rfi_mode == 2) fb_raw = fopen (fbfile, "wb");
           } else
             fb_main = fopen (fbfile, "wb");
-          if (!fb_main || (cfg.rfi_mode == 2 && !fb_raw)) { logmsg ("ERR", "cannot open output file in %s\n", datadir); exit_status = 1; aborted = 1; vf_ring_block_read_close (ring); break; }
+          if (!fb_main || (cfg.rfi_mode == 2 && !fb_raw)) { logmsg ("ERR", "cannot open output file in %s\n", datadir); exit_status = 1; aborted = 1; blocks_open++; break; }
           vf_write_sigproc_header (fb_main, &obs, vh, cfg.nbit, cfg.npol);
           if (fb_raw) vf_write_sigproc_header (fb_raw, &obs, vh, cfg.nbit, cfg.npol);
           char dh[VF_RING_HEADER_SIZE];
@@ -324,17 +325,10 @@ int main (int argc, char **argv)
         if (rc) { logmsg ("ERR", "submit failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; break; }
         pend_slot[slot] = 1;
       }
-      /* the block goes back to the writer: drain the two segments that still read from it */
-      for (int k = 0; k < 2; ++k) {
-        const int slot = (int) ((seg_counter + k) & 1);
-        if (!pend_slot[slot]) continue;
-        rc = vf_wait (h, slot);
-        pend_slot[slot] = 0;
-        if (rc) { logmsg ("ERR", "segment failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; continue; }
-        if (fb_main) fwrite (obuf[slot][0], 1, out_bytes, fb_main);
-        if (fb_raw) fwrite (obuf[slot][1], 1, out_bytes, fb_raw);
-      }
-      vf_ring_block_read_close (ring);
+      /* two segments of this block are still in flight: it stays open, and the block before it
+       * (whose segments have all been waited for by now) goes back to the writer */
+      if (blocks_open == 1) { vf_ring_block_read_close (ring); blocks_open = 0; }
+      blocks_open++;
       if (aborted) break;
       seconds_done++;
       if (seconds_done % 10 == 0) {                               /* RT_PROFILE watchdog, :1461-1477 */
@@ -344,6 +338,18 @@ int main (int argc, char **argv)
       }
       if (g_quit) break;
     }
+    /* end of the observation: drain the segments in flight, release the blocks */
+    for (int k = 0; k < 2; ++k) {
+      const int slot = (int) ((seg_counter + k) & 1);
+      if (!pend_slot[slot]) continue;
+      rc = vf_wait (h, slot);
+      pend_slot[slot] = 0;
+      if (rc) { logmsg ("ERR", "segment failed: %s\n", vf_last_error (h)); exit_status = 1; continue; }
+      if (fb_main) fwrite (obuf[slot][0], 1, out_bytes, fb_main);
+      if (fb_raw) fwrite (obuf[slot][1], 1, out_bytes, fb_raw);
+    }
+    while (blocks_open > 0) { vf_ring_block_read_close (ring); blocks_open--; }
+    if (!aborted) { uint64_t nb; while (vf_ring_block_read_open (ring, &nb)) vf_ring_block_read_close (ring); }   /* reach EOD */
     if (fb_main) fclose (fb_main);
     if (fb_raw) fclose (fb_raw);
     const double wall = now_s () - t_obs;

@@ -11,7 +11,8 @@ struct vf_ring {
   int own_mem;
   uint64_t *fill;               /* bytes valid in each block */
   unsigned char *eod;           /* block is the last one of its observation */
-  uint64_t w_idx, r_idx;        /* blocks written / read so far */
+  uint64_t w_idx, r_idx;        /* blocks written / released so far */
+  uint64_t p_idx;               /* blocks handed to the reader so far (>= r_idx: several may be open) */
   uint64_t w_off;               /* byte-stream writer: offset inside the open block */
   uint64_t r_off;               /* byte-stream reader: offset inside the open block */
   int w_open, r_open;
@@ -157,14 +158,19 @@ const void *vf_ring_block_read_open (vf_ring *r, uint64_t *nbytes)
   pthread_mutex_lock (&r->mu);
   for (;;) {
     if (r->at_eod || r->shut) { pthread_mutex_unlock (&r->mu); if (nbytes) *nbytes = 0; return NULL; }
-    if (r->w_idx > r->r_idx) {
-      const uint64_t b = r->r_idx % r->nbufs;
-      if (r->fill[b] == 0 && r->eod[b]) {          /* empty EOD block */
-        r->r_idx++; r->at_eod = 1;
+    if (r->w_idx > r->p_idx) {
+      const uint64_t b = r->p_idx % r->nbufs;
+      if (r->fill[b] == 0 && r->eod[b] && r->p_idx == r->r_idx) {   /* empty EOD block, nothing else open */
+        r->r_idx++; r->p_idx++; r->at_eod = 1;
         pthread_cond_broadcast (&r->cv);
         continue;
       }
-      r->r_open = 1; r->r_off = 0;
+      if (r->fill[b] == 0 && r->eod[b]) {          /* empty EOD block behind open blocks: end of data for now */
+        pthread_mutex_unlock (&r->mu);
+        if (nbytes) *nbytes = 0;
+        return NULL;
+      }
+      r->p_idx++; r->r_open++; r->r_off = 0;
       if (nbytes) *nbytes = r->fill[b];
       pthread_mutex_unlock (&r->mu);
       return r->mem + b * r->bufsz;
@@ -177,9 +183,9 @@ int vf_ring_block_read_close (vf_ring *r)
 {
   pthread_mutex_lock (&r->mu);
   if (!r->r_open) { pthread_mutex_unlock (&r->mu); return -1; }
-  const uint64_t b = r->r_idx % r->nbufs;
+  const uint64_t b = r->r_idx % r->nbufs;      /* blocks are released oldest first */
   if (r->eod[b]) r->at_eod = 1;
-  r->r_idx++; r->r_open = 0; r->r_off = 0;
+  r->r_idx++; r->r_open--; r->r_off = 0;
   pthread_cond_broadcast (&r->cv);
   pthread_mutex_unlock (&r->mu);
   return 0;

@@ -49,7 +49,9 @@ ssize_t vf_ring_write (vf_ring *r, const void *src, size_t n);     /* ipcio_writ
 int vf_ring_end_of_data (vf_ring *r);                              /* flushes a partial block and marks EOD */
 
 /* data blocks, reader */
-const void *vf_ring_block_read_open (vf_ring *r, uint64_t *nbytes);/* NULL at EOD (then the next header may be read) */
+/* Several blocks may be open at once (each open returns the next one); close releases the OLDEST
+ * open block to the writer.  NULL at EOD (then the next header may be read). */
+const void *vf_ring_block_read_open (vf_ring *r, uint64_t *nbytes);
 int vf_ring_block_read_close (vf_ring *r);
 ssize_t vf_ring_read (vf_ring *r, void *dst, size_t n);            /* ipcio_read: short count only at EOD */
 
