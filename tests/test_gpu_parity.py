@@ -186,10 +186,13 @@ def test_k1_thread_variants_agree(pkg):
     T = 16
     p0, p1 = make_input(pkg, T, seed=60, **RFI)
     outs = []
-    for nt in (320, 640):
-        with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, k1_threads=nt) as p:
-            outs.append(p.process_segment(p0, p1))
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for nt in (320, 512, 640):
+        with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, k1_threads=nt, keep_stats=1, do_histo=1) as p:
+            outs.append(p.process_segment(p0, p1) + (p.get_mask(), p.get_stats()))
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) and np.array_equal(outs[0][2], o[2])
+        for k in ("pow", "kur", "dag", "pow_fb", "kur_fb", "dag_fb", "weights", "histo"):
+            assert np.array_equal(outs[0][3][k], o[3][k], equal_nan=True), k
 
 
 def test_coadd_single_process(pkg, orc):
@@ -246,3 +249,62 @@ def test_coadd_batch_of_segments(pkg, orc):
         assert fb.shape == (nseg, T // 8 * 4096)
         with pytest.raises(pkg.VfError):
             p.coadd_batch(0, n, 5)
+
+
+def test_vdif_missing_and_invalid_frames_become_dropped_samples(pkg, orc):
+    """frames the writer never delivered (absent, or marked invalid) are zeros = dropped data"""
+    T = 16
+    nfr = T * 12500 // 5000
+    g = pkg.GenParams.default(seed=15, **RFI)
+    frames = pkg.gen_vdif_second(g, 0, 99, 0, nfr).reshape(-1, 5032).copy()
+    p0 = pkg.gen_samples(g, 0, 0, 99 * 25600 * 5000, T * 12500).copy()
+    p1 = pkg.gen_samples(g, 0, 1, 99 * 25600 * 5000, T * 12500).copy()
+    # frame pair 3 is absent, frame 7 of thread 1 carries the VDIF invalid bit
+    keep = np.ones(frames.shape[0], bool)
+    keep[6] = keep[7] = False
+    frames[15, 3] |= 0x80                      # word0 bit 31 (little endian: top bit of byte 3)
+    p0[3 * 5000:4 * 5000] = 0; p1[3 * 5000:4 * 5000] = 0
+    p1[7 * 5000:8 * 5000] = 0
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, keep_stats=1) as p:
+        want = p.process_segment(p0, p1)
+        wmask = p.get_mask()
+        p.reset_bandpass()
+        got = p.process_vdif(np.ascontiguousarray(frames[keep]).reshape(-1), 0)
+        assert np.array_equal(p.get_mask(), wmask)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert np.count_nonzero(wmask) > 0
+
+
+def test_batch_statistics_are_per_antenna(pkg, orc):
+    T, n = 16, 2
+    ins = [make_input(pkg, T, seed=31, antenna=a, **RFI) for a in range(n)]
+    with pkg.Pipeline(ffts_per_seg=T, nbit=2, rfi_mode=1, n_antennas=n, keep_stats=1, do_histo=1, keep_power=1) as p:
+        p.process_batch([i[0] for i in ins], [i[1] for i in ins])
+        for a in range(n):
+            o = orc.OracleChain(T, 2, 1, 1)
+            o.process_segment(*ins[a])
+            st = p.get_stats(a)
+            assert np.array_equal(p.get_mask(a), o.mask())
+            for k in ("pow", "kur", "weights", "histo"):
+                assert np.array_equal(st[k], o.get(k), equal_nan=True), (a, k)
+            assert np.abs(p.get_power_f32(a, 0) - o.ave_trimmed("main")).max() < 2e-4
+
+
+def test_argument_errors(pkg):
+    with pkg.Pipeline(ffts_per_seg=8, rfi_mode=2, n_antennas=1) as p:
+        z = np.zeros(8 * 12500, np.uint8)
+        with pytest.raises(pkg.VfError) as e:
+            p.process_segment(z[:-1], z[:-1])                 # wrong segment length
+        assert e.value.code == 1
+        with pytest.raises(pkg.VfError) as e:
+            p.process_batch([z, z], [z, z])                   # more antennas than the handle has
+        assert e.value.code == 1
+        with pytest.raises(pkg.VfError) as e:
+            p.get_power_f32()                                 # keep_power not set
+        assert e.value.code == 22
+        with pytest.raises(pkg.VfError) as e:
+            p.set_frb_injection(0)                            # inject_frb not set
+        assert e.value.code == 22
+    with pytest.raises(pkg.VfError) as e:
+        pkg.Pipeline(ffts_per_seg=8, gpu_id=99)
+    assert e.value.code == 25
