@@ -62,6 +62,7 @@ struct vf_handle {
   size_t out_bytes;           /* per antenna per stream per segment */
   size_t tile_elems;          /* T*4096 per antenna */
   cudaStream_t ctl;
+  cudaStream_t coadd_st;      /* co-add runs beside the next segments, not in front of them */
   vf_slot slot[2];
   int next_slot;              /* slot of the next synchronous segment */
   int last_slot;              /* slot that holds the last processed segment */
@@ -205,6 +206,7 @@ int vf_destroy (vf_handle *h)
     if (h->ev_kc[i]) cudaEventDestroy (h->ev_kc[i]);
   }
   if (h->ctl) cudaStreamDestroy (h->ctl);
+  if (h->coadd_st) cudaStreamDestroy (h->coadd_st);
   free (h);
   return VF_OK;
 }
@@ -254,6 +256,7 @@ int vf_create (const vf_config *cfg, vf_handle **out)
   h->nsm = prop.multiProcessorCount;
   CK (vf_k1_configure ());
   CK (cudaStreamCreateWithFlags (&h->ctl, cudaStreamNonBlocking));
+  CK (cudaStreamCreateWithFlags (&h->coadd_st, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     int rc = vf_alloc_slot (h, &h->slot[i]);
     if (rc) return rc;
@@ -618,6 +621,7 @@ int vf_sync (vf_handle *h)
   CK (cudaStreamSynchronize (h->ctl));
   CK (cudaStreamSynchronize (h->slot[0].st));
   CK (cudaStreamSynchronize (h->slot[1].st));
+  CK (cudaStreamSynchronize (h->coadd_st));
   return VF_OK;
 }
 
@@ -871,7 +875,7 @@ int vf_coadd_batch (vf_handle *h, int root, int total_antennas, int n_seg, uint8
   CK (cudaSetDevice (h->cfg.gpu_id));
   const size_t n = (size_t) h->cfg.npol * h->ntime * VF_NCHANOUT;        /* one tile */
   const size_t out1 = n * h->cfg.nbit / 8;
-  cudaStream_t st = h->ctl;
+  cudaStream_t st = h->coadd_st;
   /* after every K2 that wrote the tiles */
   if (h->have_k2_last) CK (cudaStreamWaitEvent (st, h->ev_k2_last, 0));
   /* local sum over this handle's antennas, segment by segment in time order */
