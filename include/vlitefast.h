@@ -137,6 +137,9 @@ int vf_last_elapsed_ms (vf_handle *h, float *total_ms, float *k1_ms, float *k2_m
 /* profiling aid: serial != 0 stops consecutive segments from overlapping, which makes k1_ms / k2_ms
  * above pure kernel execution times (with overlap they include waiting for SMs) */
 int vf_set_serial (vf_handle *h, int serial);
+/* self-check: the normaliser divides with a packed, branch-free sequence; this runs it beside CUDA's
+ * correctly rounded division on n (even) operand pairs p / b so that a test can compare the bits */
+int vf_debug_division (vf_handle *h, const float *p, const float *b, float *q_packed, float *q_ref, size_t n);
 
 /* pinned host memory helpers (cudaMallocHost, :578-579) */
 int vf_host_alloc (void **p, size_t bytes);

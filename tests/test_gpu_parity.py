@@ -308,3 +308,26 @@ def test_argument_errors(pkg):
     with pytest.raises(pkg.VfError) as e:
         pkg.Pipeline(ffts_per_seg=8, gpu_id=99)
     assert e.value.code == 25
+
+
+def test_packed_division_is_correctly_rounded(pkg):
+    """the normaliser's packed division against CUDA's div.rn.f32, bit for bit"""
+    rng = np.random.default_rng(3)
+    n = 1 << 22
+    p = np.exp(rng.uniform(np.log(1e-3), np.log(1e9), n)).astype(np.float32)
+    b = np.exp(rng.uniform(np.log(1e-2), np.log(1e8), n)).astype(np.float32)
+    p[:64] = 0.0
+    p[64:128] = np.inf
+    b[128:192] = 1e-35            # outside the fast range: plain division
+    b[192:256] = 1e32
+    p[256:512] = b[256:512] * np.float32(11.0)
+    p[512:768] = np.nextafter(b[512:768], np.float32(np.inf))
+    with pkg.Pipeline(ffts_per_seg=8) as pl:
+        qp, qr = pl.debug_division(p, b)
+    ok = (qp.view(np.uint32) == qr.view(np.uint32)) | (np.isnan(qp) & np.isnan(qr))
+    ok[64:128] = True             # +inf dividends: the quotient is never used (weight 0)
+    assert ok.all(), (int((~ok).sum()), p[~ok][:4], b[~ok][:4], qp[~ok][:4], qr[~ok][:4])
+    with np.errstate(all="ignore"):
+        want = (p.astype(np.float64) / b.astype(np.float64)).astype(np.float32)
+    sel = np.isfinite(want) & (want > 1e-30)
+    assert np.array_equal(qr[sel], want[sel])

@@ -67,6 +67,7 @@ def lib():
     L.vf_process_device.argtypes = [vp, i, i, vp, vp, vp]
     L.vf_sync.argtypes = [vp]
     L.vf_set_serial.argtypes = [vp, i]
+    L.vf_debug_division.argtypes = [vp, vp, vp, vp, vp, sz]
     fp = C.POINTER(C.c_float)
     L.vf_last_elapsed_ms.argtypes = [vp, fp, fp, fp]
     L.vf_host_alloc.argtypes = [C.POINTER(vp), sz]
@@ -237,6 +238,12 @@ class Pipeline:
     def process_device(self, n_ant, n_seg, d_in, d_main, d_raw=None):
         """device pointers (ints); asynchronous, see sync()."""
         self._ck(self.L.vf_process_device(self.h, n_ant, n_seg, d_in, d_main, d_raw))
+
+    def debug_division(self, p, b):
+        p = np.ascontiguousarray(p, np.float32); b = np.ascontiguousarray(b, np.float32)
+        qp = np.empty_like(p); qr = np.empty_like(p)
+        self._ck(self.L.vf_debug_division(self.h, _ptr(p), _ptr(b), _ptr(qp), _ptr(qr), p.size))
+        return qp, qr
 
     def set_serial(self, serial):
         self._ck(self.L.vf_set_serial(self.h, int(serial)))

@@ -606,6 +606,24 @@ int vf_process_device (vf_handle *h, int n_ant, int n_seg, const uint8_t *d_in,
   return vf_timing_end (h);
 }
 
+/* self-check of the packed division used by the normaliser: q_packed from the kernel's own routine,
+ * q_ref from CUDA's div.rn.f32, for n (even) host operand pairs p / b */
+int vf_debug_division (vf_handle *h, const float *p, const float *b, float *q_packed, float *q_ref, size_t n)
+{
+  if (!h || !p || !b || !q_packed || !q_ref || (n & 1)) return VF_ERR_ARG;
+  CK (cudaSetDevice (h->cfg.gpu_id));
+  float *d = NULL;
+  CK (cudaMalloc ((void **) &d, 4 * n * sizeof (float)));
+  CK (cudaMemcpy (d, p, n * sizeof (float), cudaMemcpyHostToDevice));
+  CK (cudaMemcpy (d + n, b, n * sizeof (float), cudaMemcpyHostToDevice));
+  CK (vf_launch_debug_div (d, d + n, d + 2 * n, d + 3 * n, n, h->ctl));
+  CK (cudaStreamSynchronize (h->ctl));
+  CK (cudaMemcpy (q_packed, d + 2 * n, n * sizeof (float), cudaMemcpyDeviceToHost));
+  CK (cudaMemcpy (q_ref, d + 3 * n, n * sizeof (float), cudaMemcpyDeviceToHost));
+  cudaFree (d);
+  return VF_OK;
+}
+
 /* serial != 0: segments do not overlap (K1 of segment n+1 waits for K2 of segment n), so that the
  * per-kernel times of vf_last_elapsed_ms are pure execution times.  Also set by VF_SERIAL=1. */
 int vf_set_serial (vf_handle *h, int serial)

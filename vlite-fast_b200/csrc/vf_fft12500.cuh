@@ -20,8 +20,11 @@
  *           in/out  W[S k1 + 20 k2 + p']  ->  W[S k1 + 20 k2 + k3]
  *
  * so Z[k] ends at  pos (k) = S (k mod 25) + 20 ((k / 25) mod 25) + k / 625.
- * S = 501: the 500-element blocks are padded by one element so that threads
- * which walk k1 (pass 3, detection) fall on distinct shared-memory banks.
+ * S = 505: the 500-element blocks are padded so that threads which walk k1
+ * (passes 2 and 3, detection) fall on distinct shared-memory banks: a float2
+ * occupies 2 of the 32 banks, S mod 16 = 9 is odd, and 25 S = 1 (mod 16), so in
+ * pass 2 (thread b -> k1 = b mod 25, p' = b / 25) the step from (k1 = 24, p')
+ * to (k1 = 0, p' + 1) continues the same progression of banks.
  * A 500-sample kurtosis block (src/pb_kernels.cu:243-295) is exactly input j of
  * every pass-1 butterfly, so excision is "drop input j".
  *
@@ -50,7 +53,7 @@
 #define VF_NFFT      12500
 #define VF_NA        500     /* butterflies in passes 1 and 2 */
 #define VF_NC        625     /* butterflies in pass 3 */
-#define VF_WS        501     /* padded block stride of W */
+#define VF_WS        505     /* padded block stride of W (see below) */
 #define VF_WLEN      (25 * VF_WS)
 
 /* ---- packed fp32 arithmetic ---------------------------------------------- *
@@ -256,10 +259,10 @@ VF_HD void vf_pass1 (int p, const uint8_t *b0, const uint8_t *b1, uint32_t zero_
   vf_dft25_rows_store (v, tb.tw1[p], tb.tw5[p], W + p, VF_WS);
 }
 
-/* pass 2: butterfly b in [0,500): block k1 = b / 20, offset p' = b % 20; in place */
+/* pass 2: butterfly b in [0,500): offset p' = b / 25, block k1 = b % 25; in place */
 VF_HD void vf_pass2 (int b, const vf_fft_tables &tb, float2 *W)
 {
-  const int k1 = b / 20, pp = b - 20 * k1;
+  const int pp = b / 25, k1 = b - 25 * pp;
   float2 *o = W + VF_WS * k1 + pp;
   float2 v[25];
 #pragma unroll

@@ -77,5 +77,6 @@ cudaError_t vf_launch_k2 (const vf_k2_params &p, cudaStream_t s);
 cudaError_t vf_launch_depack (const vf_depack_params &p, cudaStream_t s);
 cudaError_t vf_launch_coadd (const vf_coadd_params &p, cudaStream_t s);
 cudaError_t vf_launch_accum (float *dst, const float *src, size_t n, cudaStream_t s);
+cudaError_t vf_launch_debug_div (const float *p, const float *b, float *q_packed, float *q_ref, size_t n, cudaStream_t s);
 size_t vf_k1_smem_bytes (void);
 cudaError_t vf_k1_configure (void);
