@@ -220,3 +220,27 @@ def test_generator_is_deterministic_and_framed(pkg):
         assert w[0] == 77 and (w[1] & 0xFFFFFF) == 10 + i // 2 and ((w[3] >> 16) & 0x3FF) == i % 2 and (w[3] & 0xFFFF) == 2
         want = pkg.gen_samples(g, 2, i % 2, (77 * 25600 + 10 + i // 2) * 5000, 5000)
         assert np.array_equal(fr[i, 32:], want)
+
+
+def test_control_commands_over_udp(H):
+    """get_cmds / test_for_cmd of src/utils.c:174-220 over a UDP socket (unicast here: the build
+    container has no multicast route; a multicast group additionally joins the group)"""
+    H.vf_mc_open.argtypes = [C.c_char_p, C.c_int]
+    H.vf_mc_send.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    H.vf_get_cmds.argtypes = [C.POINTER(C.c_int * 5), C.c_int]
+    import socket as pysock, time
+    s = pysock.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    sock = H.vf_mc_open(b"127.0.0.1", port)
+    assert sock >= 0
+    assert H.vf_test_for_cmd(ord("Q"), sock) == 0                # nothing queued, does not block
+    assert H.vf_mc_send(b"127.0.0.1", port, b"NS", 2) == 2
+    time.sleep(0.05)
+    cmds = (C.c_int * 5)()
+    H.vf_get_cmds(C.byref(cmds), sock)
+    assert list(cmds) == [1, 0, 0, 0, 1]
+    assert H.vf_mc_send(b"127.0.0.1", port, b"E", 1) == 1
+    assert H.vf_mc_send(b"127.0.0.1", port, b"Q", 1) == 1
+    time.sleep(0.05)
+    assert H.vf_test_for_cmd(ord("Q"), sock) == 1                # searches every queued datagram
+    assert H.vf_test_for_cmd(ord("Q"), sock) == 0
+    H.vf_mc_close(sock)

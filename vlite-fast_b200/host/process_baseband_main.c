@@ -32,6 +32,7 @@
 #include <time.h>
 #include <unistd.h>
 #include "vlitefast.h"
+#include "vf_control.h"
 #include "vf_genbase.h"
 #include "vf_ring.h"
 #include "vf_sigproc.h"
@@ -90,7 +91,9 @@ static void usage (void)
     "  -g GPU    CUDA device [0]\n"
     "  -o        log to stderr as well\n"
     "  -l FILE   log file\n"
-    "  -j        print a one-line JSON summary on stdout at exit\n");
+    "  -j        print a one-line JSON summary on stdout at exit\n"
+    "  -m GROUP[:PORT]  listen for one-character commands (Q = quit) on this UDP multicast group\n"
+    "            (the reference listens on 224.3.29.71:20000); a unicast address binds the port only\n");
 }
 
 typedef struct {
@@ -172,7 +175,9 @@ int main (int argc, char **argv)
   vf_config cfg;
   vf_config_default (&cfg);
   int c;
-  while ((c = getopt (argc, argv, "hf:S:L:e:Fa:n:D:w:b:P:r:isg:ol:jk:K:C:p:")) != -1) {
+  char mc_group[64] = "";
+  int mc_port = VF_MC_READER_PORT, mc_sock = -1;
+  while ((c = getopt (argc, argv, "hf:S:L:e:Fa:n:D:w:b:P:r:isg:ol:jk:K:C:p:m:")) != -1) {
     switch (c) {
       case 'h': usage (); return 0;
       case 'f': file = optarg; break;
@@ -199,6 +204,12 @@ int main (int argc, char **argv)
       case 'o': g_stdout = 1; break;
       case 'l': logfile = optarg; break;
       case 'j': json = 1; break;
+      case 'm': {
+        strncpy (mc_group, optarg, sizeof (mc_group) - 1);
+        char *colon = strchr (mc_group, ':');
+        if (colon) { *colon = 0; mc_port = atoi (colon + 1); }
+        break;
+      }
       case 'k': case 'K': case 'C': case 'p': break;              /* psrdada keys / port of the reference: accepted, unused */
       default: usage (); return 1;
     }
@@ -207,6 +218,11 @@ int main (int argc, char **argv)
   if (logfile) g_log = fopen (logfile, "a");
   signal (SIGINT, on_signal);
   signal (SIGTERM, on_signal);
+  if (mc_group[0]) {                                              /* :764-768 */
+    mc_sock = vf_mc_open (mc_group, mc_port);
+    if (mc_sock < 0) logmsg ("ERR", "cannot open control socket %s:%d\n", mc_group, mc_port);
+    else logmsg ("INFO", "listening for commands on %s:%d\n", mc_group, mc_port);
+  }
 
   vf_handle *h = NULL;
   int rc = vf_create (&cfg, &h);
@@ -252,7 +268,11 @@ int main (int argc, char **argv)
     char inhdr[VF_RING_HEADER_SIZE];
     logmsg ("INFO", "Waiting for DADA header.\n");
     int hr;
-    while ((hr = vf_ring_header_read (ring, inhdr, 200)) == 1 && !g_quit) ;
+    while ((hr = vf_ring_header_read (ring, inhdr, 200)) == 1 && !g_quit) {
+      int cmds[5];
+      vf_get_cmds (cmds, mc_sock);                                /* :793-795 */
+      if (cmds[2]) { logmsg ("INFO", "Received CMD_QUIT.  Exiting.\n"); g_quit = 1; }
+    }
     if (hr != 0) break;
     logmsg ("INFO", "psrdada header:\n%s", inhdr);
     logmsg ("INFO", "Beginning new observation.\n");
@@ -336,6 +356,10 @@ int main (int argc, char **argv)
         if (wall - seconds_done > 0.5)
           logmsg ("ERR", "Falling behind real time: %.2f s wall for %ld s of data.\n", wall, seconds_done);
       }
+      if (vf_test_for_cmd (VF_CMD_QUIT, mc_sock)) {                 /* once per second, :1081-1092 */
+        logmsg ("INFO", "Received CMD_QUIT, indicating data taking is ceasing.  Exiting.\n");
+        g_quit = 1;
+      }
       if (g_quit) break;
     }
     /* end of the observation: drain the segments in flight, release the blocks */
@@ -366,6 +390,7 @@ int main (int argc, char **argv)
             "\"nbit\": %d, \"npol\": %d, \"rfi_mode\": %d, \"bytes_in\": %.0f, \"exit\": %d}\n",
             total_data_s, total_segments, total_wall_s, total_wall_s > 0 ? total_data_s / total_wall_s : 0.0,
             cfg.nbit, cfg.npol, cfg.rfi_mode, total_data_s * (double) SEC_BYTES, exit_status | fa.rc);
+  vf_mc_close (mc_sock);
   vf_ring_destroy (ring);
   for (int s = 0; s < 2; ++s) for (int k = 0; k < 2; ++k) vf_host_free (obuf[s][k]);
   vf_host_free (ring_mem);
