@@ -64,7 +64,8 @@ typedef struct vf_config {
   int inject_frb;      /* 0      -i: allow vf_set_frb_injection                     */
   int gpu_id;          /* 0      -g                                                 */
   int n_antennas;      /* 1      antennas batched on this handle                    */
-  int k1_threads;      /* 0      0 = library default (640); 320, 512 or 640 (tuning) */
+  int k1_threads;      /* 0      0 = pipelined channeliser (default); 320, 512 or 640 = monolithic
+                                 channeliser with that many threads (A/B comparison)          */
   int power_segments;  /* 0      f32 tiles kept for this many consecutive segments (0 = 1): lets
                                  vf_coadd_batch reduce a whole second in one collective       */
   int reserved[6];

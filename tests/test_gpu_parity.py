@@ -183,12 +183,20 @@ def test_device_resident_equals_host(pkg):
 
 
 def test_k1_thread_variants_agree(pkg):
-    T = 16
+    """the pipelined channeliser (0, the default) and the monolithic one at three CTA sizes give the same bits;
+    T = 1024 x 2 antennas makes every CTA of the pipelined kernel draw many items from the shared counter"""
+    for T, n_seg in ((16, 1), (1024, 3)):
+        _k1_variants(pkg, T, n_seg)
+
+
+def _k1_variants(pkg, T, n_seg):
     p0, p1 = make_input(pkg, T, seed=60, **RFI)
     outs = []
-    for nt in (320, 512, 640):
+    for nt in (0, 320, 512, 640) if T == 16 else (0, 640):
         with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, k1_threads=nt, keep_stats=1, do_histo=1) as p:
-            outs.append(p.process_segment(p0, p1) + (p.get_mask(), p.get_stats()))
+            for _ in range(n_seg):          # several launches: the item counter is never reset
+                o = p.process_segment(p0, p1)
+            outs.append(o + (p.get_mask(), p.get_stats()))
     for o in outs[1:]:
         assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) and np.array_equal(outs[0][2], o[2])
         for k in ("pow", "kur", "dag", "pow_fb", "kur_fb", "dag_fb", "weights", "histo"):

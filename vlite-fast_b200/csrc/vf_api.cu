@@ -39,6 +39,8 @@ struct vf_slot {
   int pending;                /* vf_submit_*_async issued, vf_wait not yet called */
   unsigned int *d_bad, *h_bad;/* frames outside the window (VDIF input) */
   uint32_t first_frame;
+  unsigned int *d_work;       /* item counter of the pipelined channeliser; never reset: */
+  unsigned int work_base;     /* its value when the next launch starts                   */
 };
 
 /* minimal NCCL surface, resolved with dlopen at vf_coadd_init */
@@ -171,6 +173,9 @@ static int vf_alloc_slot (vf_handle *h, vf_slot *s)
   CK (cudaMalloc ((void **) &s->mask, na * h->T * sizeof (uint32_t)));
   CK (cudaMemset (s->w, 0, na * h->T * sizeof (float)));
   CK (cudaMemset (s->mask, 0, na * h->T * sizeof (uint32_t)));
+  CK (cudaMalloc ((void **) &s->d_work, sizeof (unsigned int)));
+  CK (cudaMemset (s->d_work, 0, sizeof (unsigned int)));
+  s->work_base = 0;
   CK (cudaMalloc ((void **) &s->d_out_main, na * h->out_bytes));
   if (mode == 2) CK (cudaMalloc ((void **) &s->d_out_raw, na * h->out_bytes));
   CK (cudaEventCreateWithFlags (&s->ev_k2, cudaEventDisableTiming));
@@ -189,6 +194,7 @@ int vf_destroy (vf_handle *h)
     cudaFree (s->d_in); cudaFree (s->d_frames); cudaFree (s->P_raw); cudaFree (s->P_kur);
     cudaFree (s->w); cudaFree (s->mask); cudaFree (s->d_out_main); cudaFree (s->d_out_raw);
     cudaFree (s->d_bad); if (s->h_bad) cudaFreeHost (s->h_bad);
+    cudaFree (s->d_work);
     if (s->ev_k2) cudaEventDestroy (s->ev_k2);
     if (s->ev_done) cudaEventDestroy (s->ev_done);
     if (s->st) cudaStreamDestroy (s->st);
@@ -369,7 +375,12 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
   if (h->histo) CK (cudaMemsetAsync (h->histo, 0, (size_t) n_ant * 512 * sizeof (unsigned int), s->st));
   const int n_items = n_ant * h->T;
   const int grid = n_items < h->nsm ? n_items : h->nsm;
-  const int threads = c.k1_threads ? c.k1_threads : 640;
+  const int threads = c.k1_threads;            /* 0: pipelined kernel; 320/512/640: monolithic kernel (A/B) */
+  if (threads == 0) {
+    k1.work_counter = s->d_work;
+    k1.work_base = s->work_base;
+    s->work_base += (unsigned int) (n_items + 2 * grid);   /* what this launch draws (wraps with the counter) */
+  }
   if (h->serial && h->have_k2_last) CK (cudaStreamWaitEvent (s->st, h->ev_k2_last, 0));
   if (timed >= 0) CK (cudaEventRecord (h->ev_ka[timed], s->st));
   CK (vf_launch_k1 (k1, grid, threads, s->st));

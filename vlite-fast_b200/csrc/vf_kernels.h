@@ -38,7 +38,8 @@ struct vf_k1_params {
   const float *frb_delays;    /* optional [6251]; FRB injection, src/pb_kernels.cu:348-391 */
   int nfft_since_frb;
   float frb_width, frb_amp;
-  unsigned int *work_counter; /* dynamic work distribution */
+  unsigned int *work_counter; /* pipelined kernel: items are drawn from this counter ... */
+  unsigned int work_base;     /* ... whose value at launch was work_base (it advances by n_items + 2 * grid) */
 };
 
 /* Normaliser: bandpass IIR + pscrunch + tscrunch + select/digitise. */

@@ -31,9 +31,16 @@ extern "C" {
 
 typedef struct vf_ring vf_ring;
 
-/* mem == NULL: malloc the data area (nbufs * bufsz bytes) */
+/* in-process ring; mem == NULL: malloc the data area (nbufs * bufsz bytes); nbufs <= 1024 */
 vf_ring *vf_ring_create (uint64_t nbufs, uint64_t bufsz, void *mem);
+/* ring in a SysV shared-memory segment, shared between processes the way psrdada's are:
+ * create = "dada_db -k key -b bufsz -n nbufs" (fails if the key exists), connect =
+ * dada_hdu_connect, remove = "dada_db -d".  The creator's vf_ring_destroy removes the segment. */
+vf_ring *vf_ring_create_shm (int key, uint64_t nbufs, uint64_t bufsz);
+vf_ring *vf_ring_connect_shm (int key);
+int vf_ring_remove_shm (int key);
 void vf_ring_destroy (vf_ring *r);
+void *vf_ring_data_base (const vf_ring *r);        /* first data block (to page-lock the ring for DMA) */
 uint64_t vf_ring_get_nbufs (const vf_ring *r);
 uint64_t vf_ring_get_bufsz (const vf_ring *r);
 uint64_t vf_ring_get_nfull (vf_ring *r);
