@@ -405,6 +405,7 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
   /* bp_scale = float(tsamp/tsmooth), src/process_baseband.cu:737-741 */
   k2.bp_scale = (float) (((double) VF_NFFT / 128000000 * VF_NSCRUNCH) / 1.0);
   k2.out_main = d_main; k2.out_raw = d_raw; k2.out_stride = h->out_bytes;
+  { static const char *dbg = getenv ("VF_K2_DEBUG"); k2.debug = dbg ? atoi (dbg) : 0; }
   {
     /* tile slot of this segment in the ring of kept tiles (sized for the handle's n_antennas) */
     const size_t tile_all = (size_t) h->n_ant * c.npol * h->ntime * VF_NCHANOUT;
@@ -750,20 +751,22 @@ int vf_get_detected_power (vf_handle *h, int antenna, int which, float *out)
   vf_slot *s = &h->slot[h->last_slot];
   const size_t n = h->tile_elems, off = (size_t) antenna * n;
   const bool want_kur = (which == 0 && mode != 0);
-  if (!want_kur) {
-    CK (cudaMemcpy (out, s->P_raw + off, n * sizeof (float2), cudaMemcpyDeviceToHost));
-    return VF_OK;
-  }
-  CK (cudaMemcpy (out, s->P_kur + off, n * sizeof (float2), cudaMemcpyDeviceToHost));
-  if (mode == 2) {
+  /* the device tile is blocked ([4096/16][T][16], VF_PBLK): copy it out and put it in [T][4096] order */
+  std::vector<float2> blk (n), blk_raw;
+  CK (cudaMemcpy (blk.data (), (want_kur ? s->P_kur : s->P_raw) + off, n * sizeof (float2), cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> mk;
+  if (want_kur && mode == 2) {
     /* time steps with an empty mask were not re-transformed: identical to raw */
-    std::vector<uint32_t> mk (h->T);
-    std::vector<float> row (2 * VF_NCHANOUT);
+    mk.resize (h->T);
+    blk_raw.resize (n);
     CK (cudaMemcpy (mk.data (), s->mask + (size_t) antenna * h->T, (size_t) h->T * 4, cudaMemcpyDeviceToHost));
-    for (int t = 0; t < h->T; ++t)
-      if (mk[t] == 0)
-        CK (cudaMemcpy (out + (size_t) t * 2 * VF_NCHANOUT, s->P_raw + off + (size_t) t * VF_NCHANOUT,
-                        VF_NCHANOUT * sizeof (float2), cudaMemcpyDeviceToHost));
+    CK (cudaMemcpy (blk_raw.data (), s->P_raw + off, n * sizeof (float2), cudaMemcpyDeviceToHost));
+  }
+  float2 *o2 = reinterpret_cast<float2 *> (out);
+  for (int t = 0; t < h->T; ++t) {
+    const float2 *src = (!mk.empty () && mk[t] == 0) ? blk_raw.data () : blk.data ();
+    for (int c = 0; c < VF_NCHANOUT; ++c)
+      o2[(size_t) t * VF_NCHANOUT + c] = src[(size_t) t * VF_PBLK + VF_PIDX (h->T, c)];
   }
   return VF_OK;
 }

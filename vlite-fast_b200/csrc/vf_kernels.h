@@ -19,6 +19,14 @@
 #define VF_VD_DAT      5000     /* :17 */
 #define VF_FRAME_RATE  25600    /* :19 */
 
+/* Detected-power tile between the two kernels, per antenna: [4096 / VF_PBLK][T][VF_PBLK] float2.
+ * VF_PBLK = 4096 is the plain [T][4096] tile.  A blocked tile (VF_PBLK = 16: the 16 channels of a
+ * normaliser CTA contiguous over all time steps) was measured on B200 and rejected: the normaliser
+ * was no faster (its staging is latency, not locality, bound) and the channeliser's scattered
+ * 128-byte stores cost it 2 us per segment. */
+#define VF_PBLK        VF_NCHANOUT
+#define VF_PIDX(T, c)  (((size_t) ((c) / VF_PBLK) * (size_t) (T)) * VF_PBLK + ((c) % VF_PBLK))   /* relative to time step t's base (t * VF_PBLK) */
+
 #define VF_WIN         12512    /* 16-byte aligned window that covers any 12500-sample block */
 
 /* Channeliser: one work item = one FFT time step of one antenna (both pols). */
@@ -26,7 +34,7 @@ struct vf_k1_params {
   const uint8_t *in;          /* [n_ant][2][T*12500] samples, every pol 16-byte aligned */
   size_t ant_stride, pol_stride;
   int T, n_ant, rfi_mode;
-  float2 *P_raw, *P_kur;      /* [n_ant][T][4096] (pol0, pol1) detected power */
+  float2 *P_raw, *P_kur;      /* [n_ant][T][4096] (pol0, pol1) detected power (see VF_PBLK) */
   float *w;                   /* [n_ant][T] excision weight (shared by both pols) */
   uint32_t *mask;             /* [n_ant][T] bit j = sub-block j zeroed */
   float *pw, *kur, *dag;      /* optional [n_ant][2][T*25] */
@@ -53,6 +61,7 @@ struct vf_k2_params {
   uint8_t *out_main, *out_raw;/* [n_ant][out_bytes] */
   size_t out_stride;
   float *ave_main, *ave_raw;  /* optional [n_ant][npol][T/8][4096] */
+  int debug;                  /* VF_K2_DEBUG (profiling only): 1 skip fan-out, 2 skip recursion, 4 skip weight division */
 };
 
 struct vf_depack_params {
