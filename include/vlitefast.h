@@ -145,6 +145,10 @@ int vf_debug_division (vf_handle *h, const float *p, const float *b, float *q_pa
 /* pinned host memory helpers (cudaMallocHost, :578-579) */
 int vf_host_alloc (void **p, size_t bytes);
 int vf_host_free (void *p);
+/* page-lock memory the caller already owns -- e.g. the data blocks of a shared-memory ring
+ * (psrdada's dada_db -l, dada_cuda_dbregister) -- so that it can be DMA'd like vf_host_alloc memory */
+int vf_host_register (void *p, size_t bytes);
+int vf_host_unregister (void *p);
 
 /* Statistics of the last segment of `antenna` (needs keep_stats / do_histo);
  * any pointer may be NULL.  Layouts as in the reference (:622-643):

@@ -49,3 +49,36 @@ def test_synthetic_stream(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     summ = json.loads(r.stdout.strip().splitlines()[-1])
     assert summ["seconds"] == 6 and summ["segments"] == 60 and summ["x_realtime"] > 1
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "vf_dada_db")), reason="executables not built")
+def test_shared_memory_ring_matches_file_replay(tmp_path):
+    """the reference's arrangement (scripts/start_dada:13): dada_db makes the ring, a producer process fills it,
+    process_baseband -k reads it; same bytes as the file replay of the same data"""
+    key = "%x" % (0x5000 + os.getpid() % 0x1000)
+    subprocess.run([os.path.join(BIN, "vf_dada_db"), "-k", key, "-d"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([os.path.join(BIN, "vf_dada_db"), "-k", key, "-n", "3"], check=True, stdout=subprocess.DEVNULL)
+    try:
+        d_ring, d_file = tmp_path / "ring", tmp_path / "file"
+        d_ring.mkdir(); d_file.mkdir()
+        gen = ["-t", "2", "-r", "21", "-f", "-n", "6"]
+        reader = subprocess.Popen([os.path.join(BIN, "process_baseband"), "-k", key, "-s", "-D", str(d_ring), "-b", "8", "-r", "2", "-j"],
+                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        subprocess.run([os.path.join(BIN, "genbase"), "-k", key] + gen, check=True, timeout=300)
+        out, err = reader.communicate(timeout=300)
+        assert reader.returncode == 0, err[-2000:]
+        summ = json.loads(out.strip().splitlines()[-1])
+        assert summ["seconds"] == 2 and summ["segments"] == 20 and summ["exit"] == 0
+        vdif = tmp_path / "two.vdif"
+        subprocess.run([os.path.join(BIN, "genbase"), "-o", str(vdif)] + gen, check=True)
+        r = subprocess.run([os.path.join(BIN, "process_baseband"), "-f", str(vdif), "-D", str(d_file), "-b", "8", "-r", "2", "-a", "6", "-j", "-n", "2"],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        a, b = sorted(os.listdir(d_ring)), sorted(os.listdir(d_file))
+        assert len(a) == 2 and len(b) == 2
+        for fa, fb in zip(a, b):
+            da, db = open(d_ring / fa, "rb").read(), open(d_file / fb, "rb").read()
+            _, _, ua = parse_sigproc(da); _, _, ub = parse_sigproc(db)
+            assert da[ua:] == db[ub:] and len(da) - ua == 20 * 128 * 4096
+    finally:
+        subprocess.run([os.path.join(BIN, "vf_dada_db"), "-k", key, "-d"], stdout=subprocess.DEVNULL)

@@ -244,3 +244,100 @@ def test_control_commands_over_udp(H):
     assert H.vf_test_for_cmd(ord("Q"), sock) == 1                # searches every queued datagram
     assert H.vf_test_for_cmd(ord("Q"), sock) == 0
     H.vf_mc_close(sock)
+
+
+# ---- shared-memory ring (psrdada-style, between processes) -------------------
+_SHM_WRITER = r"""
+import ctypes as C, sys
+L = C.CDLL(sys.argv[1])
+L.vf_ring_connect_shm.restype = C.c_void_p; L.vf_ring_connect_shm.argtypes = [C.c_int]
+L.vf_ring_header_write.argtypes = [C.c_void_p, C.c_char_p]
+L.vf_ring_block_write_open.restype = C.c_void_p; L.vf_ring_block_write_open.argtypes = [C.c_void_p]
+L.vf_ring_block_write_close.argtypes = [C.c_void_p, C.c_uint64]
+L.vf_ring_end_of_data.argtypes = [C.c_void_p]; L.vf_ring_destroy.argtypes = [C.c_void_p]
+r = L.vf_ring_connect_shm(int(sys.argv[2]))
+assert r
+assert L.vf_ring_header_write(r, b"NAME shm\nSTATIONID 9\n") == 0
+for i in range(7):
+    p = L.vf_ring_block_write_open(r)
+    assert p
+    C.memset(p, i + 1, 4096)
+    assert L.vf_ring_block_write_close(r, 4096 if i < 6 else 100) == 0
+assert L.vf_ring_end_of_data(r) == 0
+L.vf_ring_destroy(r)
+"""
+
+
+def _shm_api(H):
+    H.vf_ring_create_shm.restype = C.c_void_p; H.vf_ring_create_shm.argtypes = [C.c_int, C.c_uint64, C.c_uint64]
+    H.vf_ring_connect_shm.restype = C.c_void_p; H.vf_ring_connect_shm.argtypes = [C.c_int]
+    H.vf_ring_remove_shm.argtypes = [C.c_int]
+    H.vf_ring_data_base.restype = C.c_void_p; H.vf_ring_data_base.argtypes = [C.c_void_p]
+    H.vf_ring_get_nbufs.restype = C.c_uint64; H.vf_ring_get_nbufs.argtypes = [C.c_void_p]
+    H.vf_ring_get_bufsz.restype = C.c_uint64; H.vf_ring_get_bufsz.argtypes = [C.c_void_p]
+
+
+def test_shm_ring_between_processes(H, pkg, tmp_path):
+    """a ring in SysV shared memory (what psrdada's dada_db makes): another process attaches by key,
+    writes an observation, this one reads it with back-pressure (3 blocks for 7 written)"""
+    import os, subprocess, sys
+    _shm_api(H)
+    key = 0x6000 + os.getpid() % 0x1000
+    H.vf_ring_remove_shm(key)
+    r = H.vf_ring_create_shm(key, 3, 4096)
+    assert r
+    assert not H.vf_ring_create_shm(key, 3, 4096)                     # the key exists: refused, like dada_db
+    try:
+        assert H.vf_ring_get_nbufs(r) == 3 and H.vf_ring_get_bufsz(r) == 4096
+        script = tmp_path / "writer.py"
+        script.write_text(_SHM_WRITER)
+        w = subprocess.Popen([sys.executable, str(script), pkg.hostlib()._name, str(key)])
+        hdr = C.create_string_buffer(4096)
+        assert H.vf_ring_header_read(r, hdr, 20000) == 0 and b"STATIONID 9" in hdr.value
+        nb = C.c_uint64()
+        for i in range(7):
+            p = H.vf_ring_block_read_open(r, C.byref(nb))
+            assert p and C.string_at(p, 2) == bytes([i + 1]) * 2
+            assert nb.value == (4096 if i < 6 else 100)
+            H.vf_ring_block_read_close(r)
+        assert not H.vf_ring_block_read_open(r, C.byref(nb))          # end of data
+        assert w.wait(timeout=20) == 0
+        assert H.vf_ring_header_read(r, hdr, 50) == 1                  # no second observation
+    finally:
+        H.vf_ring_destroy(r)                                           # the creator removes the segment
+    assert not H.vf_ring_connect_shm(key)
+
+
+def test_dada_db_and_genbase_into_ring(H, pkg, tmp_path):
+    """vf_dada_db makes the ring, genbase -k fills it from another process; the blocks equal genbase -o"""
+    import os, subprocess
+    from conftest import ROOT
+    BIN = os.path.join(ROOT, "vlite-fast_b200", "bin")
+    if not os.path.exists(os.path.join(BIN, "vf_dada_db")):
+        pytest.skip("executables not built")
+    _shm_api(H)
+    key = 0x7000 + os.getpid() % 0x1000
+    subprocess.run([os.path.join(BIN, "vf_dada_db"), "-k", "%x" % key, "-d"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out = subprocess.run([os.path.join(BIN, "vf_dada_db"), "-k", "%x" % key, "-n", "2"], check=True, stdout=subprocess.PIPE, text=True).stdout
+    assert "nbufs=2 bufsz=257638400" in out
+    try:
+        vdif = tmp_path / "one.vdif"
+        subprocess.run([os.path.join(BIN, "genbase"), "-o", str(vdif), "-t", "1", "-r", "5", "-n", "3"], check=True)
+        w = subprocess.Popen([os.path.join(BIN, "genbase"), "-k", "%x" % key, "-t", "1", "-r", "5", "-n", "3"])
+        r = H.vf_ring_connect_shm(key)
+        assert r
+        hdr = C.create_string_buffer(4096)
+        assert H.vf_ring_header_read(r, hdr, 60000) == 0
+        assert b"GENBASE" in hdr.value and b"STATIONID" in hdr.value
+        nb = C.c_uint64()
+        p = H.vf_ring_block_read_open(r, C.byref(nb))
+        assert p and nb.value == 257638400
+        got = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nb.value,))
+        assert np.array_equal(got, np.fromfile(vdif, np.uint8))
+        H.vf_ring_block_read_close(r)
+        assert not H.vf_ring_block_read_open(r, C.byref(nb))
+        assert w.wait(timeout=60) == 0
+        H.vf_ring_destroy(r)
+    finally:
+        subprocess.run([os.path.join(BIN, "vf_dada_db"), "-k", "%x" % key, "-d"], check=True, stdout=subprocess.DEVNULL)
+    assert not H.vf_ring_connect_shm(key)

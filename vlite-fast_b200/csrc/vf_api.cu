@@ -345,6 +345,21 @@ int vf_host_alloc (void **p, size_t bytes)
 
 int vf_host_free (void *p) { return cudaFreeHost (p) == cudaSuccess ? VF_OK : VF_ERR_CUDA; }
 
+int vf_host_register (void *p, size_t bytes)
+{
+  if (!p || !bytes) return VF_ERR_ARG;
+  cudaError_t e = cudaHostRegister (p, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) cudaGetLastError ();
+  return e == cudaSuccess ? VF_OK : (e == cudaErrorMemoryAllocation ? VF_ERR_NOMEM : VF_ERR_CUDA);
+}
+
+int vf_host_unregister (void *p)
+{
+  cudaError_t e = cudaHostUnregister (p);
+  if (e != cudaSuccess) cudaGetLastError ();
+  return e == cudaSuccess ? VF_OK : VF_ERR_CUDA;
+}
+
 /* ---- the launch sequence of one segment on one slot ---------------------- *
  * d_in: [n_ant][2][T*12500] on the device.  Outputs to d_main / d_raw
  * ([n_ant][out_bytes]).  timed >= 0: record the K1/K2 events of that index. */

@@ -10,9 +10,11 @@
  * (include/vlitefast.h); this file only moves frames and bytes.
  *
  * Differences from the reference, all deliberate:
- *  - psrdada is not available: the input ring is the in-process shim of
- *    vf_ring.h, fed by a thread that replays a VDIF file (-f, the reference's
- *    readbase) or synthetic seconds (-S, the reference's genbase);
+ *  - psrdada is not available: the input ring is the shim of vf_ring.h, either
+ *    a SysV shared-memory ring made by vf_dada_db and fed by another process
+ *    (-k KEY, the reference's arrangement, scripts/start_dada:13), or an
+ *    in-process one fed by a thread that replays a VDIF file (-f, the
+ *    reference's readbase) or synthetic seconds (-S, the reference's genbase);
  *  - frames are not depacketised on the host (:1034-1035): one-second ring
  *    blocks live in pinned memory and each segment is DMA'd straight from the
  *    block and depacketised on the GPU (vf_submit_vdif_async), double buffered;
@@ -75,6 +77,7 @@ static void usage (void)
 {
   fprintf (stdout,
     "Usage: process_baseband [options]\n"
+    "  -k KEY    read from the shared-memory ring with this (hexadecimal) key, made by vf_dada_db\n"
     "  -f FILE   replay a VDIF file into the input ring (readbase)\n"
     "  -S N      synthesise N distinct seconds of baseband (genbase style) instead of -f\n"
     "  -L M      replay the synthetic seconds M times (stream of N*M seconds) [1]\n"
@@ -171,6 +174,7 @@ int main (int argc, char **argv)
 {
   const char *file = NULL, *datadir = ".", *logfile = NULL;
   int synth_n = 0, loops = 1, station = 1, nbuf = 0, write_fb = 1, single = 0, json = 0, rfi_flag = 0;
+  long shm_key = -1;
   unsigned long long seed = 102;
   vf_config cfg;
   vf_config_default (&cfg);
@@ -210,11 +214,12 @@ int main (int argc, char **argv)
         if (colon) { *colon = 0; mc_port = atoi (colon + 1); }
         break;
       }
-      case 'k': case 'K': case 'C': case 'p': break;              /* psrdada keys / port of the reference: accepted, unused */
+      case 'k': shm_key = (long) strtoul (optarg, NULL, 16); break;  /* input ring key, :541-569 */
+      case 'K': case 'C': case 'p': break;                        /* output ring keys / port of the reference: accepted, unused */
       default: usage (); return 1;
     }
   }
-  if (!file && synth_n <= 0) { usage (); return 1; }
+  if (!file && synth_n <= 0 && shm_key < 0) { usage (); return 1; }
   if (logfile) g_log = fopen (logfile, "a");
   signal (SIGINT, on_signal);
   signal (SIGTERM, on_signal);
@@ -232,11 +237,24 @@ int main (int argc, char **argv)
   }
   const size_t out_bytes = vf_segment_out_bytes (h);
 
-  if (nbuf <= 0) nbuf = synth_n > 0 ? synth_n : 4;
-  if (synth_n > 0 && nbuf != synth_n) { logmsg ("ERR", "-n must equal -S for the in-place synthetic replay\n"); return 1; }
   void *ring_mem = NULL;
-  if (vf_host_alloc (&ring_mem, (size_t) nbuf * SEC_BYTES)) { logmsg ("ERR", "cannot pin %d ring blocks\n", nbuf); return 21; }
-  vf_ring *ring = vf_ring_create ((uint64_t) nbuf, SEC_BYTES, ring_mem);
+  vf_ring *ring = NULL;
+  int ring_registered = 0;
+  if (shm_key >= 0) {
+    /* dada_hdu_connect + lock_read (:541-569); the blocks are page-locked in place so that segments
+     * are DMA'd straight out of the ring (psrdada: dada_cuda_dbregister) */
+    ring = vf_ring_connect_shm ((int) shm_key);
+    if (!ring) { logmsg ("ERR", "cannot connect to the ring with key %lx\n", shm_key); return 1; }
+    if (vf_ring_get_bufsz (ring) != SEC_BYTES) { logmsg ("ERR", "ring blocks must be one second (%zu bytes)\n", SEC_BYTES); return 1; }
+    nbuf = (int) vf_ring_get_nbufs (ring);
+    if (vf_host_register (vf_ring_data_base (ring), (size_t) nbuf * SEC_BYTES) == VF_OK) ring_registered = 1;
+    else logmsg ("INFO", "could not page-lock the ring; copies will be staged by the driver\n");
+  } else {
+    if (nbuf <= 0) nbuf = synth_n > 0 ? synth_n : 4;
+    if (synth_n > 0 && nbuf != synth_n) { logmsg ("ERR", "-n must equal -S for the in-place synthetic replay\n"); return 1; }
+    if (vf_host_alloc (&ring_mem, (size_t) nbuf * SEC_BYTES)) { logmsg ("ERR", "cannot pin %d ring blocks\n", nbuf); return 21; }
+    ring = vf_ring_create ((uint64_t) nbuf, SEC_BYTES, ring_mem);
+  }
   uint8_t *obuf[2][2] = {{NULL, NULL}, {NULL, NULL}};             /* [slot][main, raw] pinned */
   for (int s = 0; s < 2; ++s)
     for (int k = 0; k < 2; ++k)
@@ -258,7 +276,8 @@ int main (int argc, char **argv)
 
   feeder_args fa = { ring, file, synth_n, loops, station, 3600u * 5, 0 };
   pthread_t feeder;
-  pthread_create (&feeder, NULL, file ? feeder_file : feeder_synth, &fa);
+  const int have_feeder = shm_key < 0;
+  if (have_feeder) pthread_create (&feeder, NULL, file ? feeder_file : feeder_synth, &fa);
 
   double total_data_s = 0, total_wall_s = 0;
   long total_segments = 0;
@@ -380,20 +399,23 @@ int main (int argc, char **argv)
     logmsg ("INFO", "Proc Time...%.3f s for %ld s of data (%.1fx real time)\n", wall, seconds_done,
             wall > 0 ? seconds_done / wall : 0.0);                /* :1534-1536 */
     total_data_s += seconds_done; total_wall_s += wall; total_segments += seg_counter;
-    if (aborted) { vf_ring_shutdown (ring); break; }
+    if (aborted) { if (have_feeder) vf_ring_shutdown (ring); break; }
     if (single || synth_n > 0 || file) break;
   }
-  vf_ring_shutdown (ring);
-  pthread_join (feeder, NULL);
+  if (have_feeder) {
+    vf_ring_shutdown (ring);
+    pthread_join (feeder, NULL);
+  }
   if (json)
     printf ("{\"program\": \"process_baseband\", \"seconds\": %.0f, \"segments\": %ld, \"wall_s\": %.6f, \"x_realtime\": %.3f, "
             "\"nbit\": %d, \"npol\": %d, \"rfi_mode\": %d, \"bytes_in\": %.0f, \"exit\": %d}\n",
             total_data_s, total_segments, total_wall_s, total_wall_s > 0 ? total_data_s / total_wall_s : 0.0,
             cfg.nbit, cfg.npol, cfg.rfi_mode, total_data_s * (double) SEC_BYTES, exit_status | fa.rc);
   vf_mc_close (mc_sock);
+  if (ring_registered) vf_host_unregister (vf_ring_data_base (ring));
   vf_ring_destroy (ring);
   for (int s = 0; s < 2; ++s) for (int k = 0; k < 2; ++k) vf_host_free (obuf[s][k]);
-  vf_host_free (ring_mem);
+  if (ring_mem) vf_host_free (ring_mem);
   vf_destroy (h);
   if (g_log) fclose (g_log);
   return exit_status | fa.rc;

@@ -113,6 +113,8 @@ int vf_ring_remove_shm (int key)
   return shmctl (id, IPC_RMID, NULL);
 }
 
+void vf_ring_disown (vf_ring *r) { if (r) r->creator = 0; }
+
 void vf_ring_destroy (vf_ring *r)
 {
   if (!r) return;

@@ -1,5 +1,5 @@
 /*
- * psrdada-style ring buffer shim (in-process).  The reference reads VDIF frames
+ * psrdada-style ring buffer shim (in-process, or between processes through SysV shared memory).  The reference reads VDIF frames
  * from a psrdada shared-memory ring fed by writer / genbase / readbase and
  * writes filterbank data to two more (src/process_baseband.cu:541-569,
  * 799-849, 1038, 1416-1422, 1482-1494); psrdada is not in this image, so this
@@ -39,6 +39,7 @@ vf_ring *vf_ring_create (uint64_t nbufs, uint64_t bufsz, void *mem);
 vf_ring *vf_ring_create_shm (int key, uint64_t nbufs, uint64_t bufsz);
 vf_ring *vf_ring_connect_shm (int key);
 int vf_ring_remove_shm (int key);
+void vf_ring_disown (vf_ring *r);                  /* the creator's vf_ring_destroy only detaches (dada_db without -d) */
 void vf_ring_destroy (vf_ring *r);
 void *vf_ring_data_base (const vf_ring *r);        /* first data block (to page-lock the ring for DMA) */
 uint64_t vf_ring_get_nbufs (const vf_ring *r);
