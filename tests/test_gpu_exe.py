@@ -82,3 +82,62 @@ def test_shared_memory_ring_matches_file_replay(tmp_path):
             assert da[ua:] == db[ub:] and len(da) - ua == 20 * 128 * 4096
     finally:
         subprocess.run([os.path.join(BIN, "vf_dada_db"), "-k", key, "-d"], stdout=subprocess.DEVNULL)
+
+
+_RING_READER = r"""
+import ctypes as C, sys
+L = C.CDLL(sys.argv[1])
+L.vf_ring_connect_shm.restype = C.c_void_p; L.vf_ring_connect_shm.argtypes = [C.c_int]
+L.vf_ring_header_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+L.vf_ring_read.restype = C.c_ssize_t; L.vf_ring_read.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+L.vf_ring_destroy.argtypes = [C.c_void_p]
+r = L.vf_ring_connect_shm(int(sys.argv[2], 16))
+hdr = C.create_string_buffer(4096)
+assert L.vf_ring_header_read(r, hdr, 120000) == 0
+open(sys.argv[3] + ".hdr", "wb").write(hdr.value)
+buf = C.create_string_buffer(1 << 20)
+with open(sys.argv[3], "wb") as f:
+    while True:
+        n = L.vf_ring_read(r, buf, len(buf))
+        f.write(buf.raw[:n])
+        if n < len(buf):
+            break
+L.vf_ring_destroy(r)
+"""
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "vf_dada_db")), reason="executables not built")
+def test_output_rings(pkg, tmp_path):
+    """-C: the main stream segment by segment (co-adder ring, src/process_baseband.cu:1416-1422);
+    -K: the first 10 s at once, then second by second (heimdall ring, :1482-1494).  Both carry the
+    psrdada header of :136-201 and, over 12 s, exactly the bytes of the _kur filterbank file."""
+    import sys
+    base = 0x4000 + (os.getpid() % 0x800) * 2
+    kout, kco = "%x" % base, "%x" % (base + 1)
+    for k in (kout, kco):
+        subprocess.run([os.path.join(BIN, "vf_dada_db"), "-k", k, "-d"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.run([os.path.join(BIN, "vf_dada_db"), "-k", k, "-b", "1310720", "-n", "16"], check=True, stdout=subprocess.DEVNULL)
+    try:
+        script = tmp_path / "reader.py"
+        script.write_text(_RING_READER)
+        lib = pkg.hostlib()._name
+        readers = [subprocess.Popen([sys.executable, str(script), lib, k, str(tmp_path / n)]) for k, n in ((kout, "out.bin"), (kco, "co.bin"))]
+        r = subprocess.run([os.path.join(BIN, "process_baseband"), "-S", "2", "-L", "6", "-F", "-D", str(tmp_path), "-b", "2", "-r", "2",
+                            "-K", kout, "-C", kco, "-j"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        for p in readers:
+            assert p.wait(timeout=60) == 0
+        fil = [f for f in os.listdir(tmp_path) if f.endswith("_kur.fil")]
+        assert len(fil) == 1
+        buf = open(tmp_path / fil[0], "rb").read()
+        _, _, used = parse_sigproc(buf)
+        data = buf[used:]
+        assert len(data) == 120 * 128 * 4096 // 4
+        assert open(tmp_path / "co.bin", "rb").read() == data
+        assert open(tmp_path / "out.bin", "rb").read() == data
+        hdr = open(tmp_path / "out.bin.hdr", "rb").read().decode()
+        assert "NCHAN 4096" in hdr.replace("  ", " ") or "NCHAN" in hdr
+        assert fil[0] in hdr                                          # SIGPROC_FILE key, :197
+    finally:
+        for k in (kout, kco):
+            subprocess.run([os.path.join(BIN, "vf_dada_db"), "-k", k, "-d"], stdout=subprocess.DEVNULL)

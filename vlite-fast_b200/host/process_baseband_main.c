@@ -78,6 +78,8 @@ static void usage (void)
   fprintf (stdout,
     "Usage: process_baseband [options]\n"
     "  -k KEY    read from the shared-memory ring with this (hexadecimal) key, made by vf_dada_db\n"
+    "  -K KEY    write the main stream to this ring: the first 10 s at once, then second by second (heimdall)\n"
+    "  -C KEY    write the main stream to this ring segment by segment (co-adder)\n"
     "  -f FILE   replay a VDIF file into the input ring (readbase)\n"
     "  -S N      synthesise N distinct seconds of baseband (genbase style) instead of -f\n"
     "  -L M      replay the synthetic seconds M times (stream of N*M seconds) [1]\n"
@@ -170,11 +172,61 @@ static void *feeder_synth (void *vp)
   return NULL;
 }
 
+/* Output rings of the reference (:306-332, :1416-1422, :1482-1494).  check_buffer: a ring with a
+ * single free block left means that the consumer has stalled; the reference gives up (exit). */
+typedef struct {
+  vf_ring *ring_out, *ring_co;
+  uint8_t *out10;
+  size_t out_bytes;
+  long done_segs;
+  int out_buf_sec;
+} out_sinks;
+
+static int ring_sink_write (vf_ring *r, const void *buf, size_t n, const char *what);
+
+/* one finished segment of the main stream: co-add ring at once (:1416-1422); heimdall ring through the
+ * 10-s buffer (:1370-1376, :1482-1494: the whole buffer after the 10th second, then each new second,
+ * which the reference puts back at the start of the buffer) */
+static int sinks_segment (out_sinks *k, const uint8_t *seg)
+{
+  if (k->ring_co && ring_sink_write (k->ring_co, seg, k->out_bytes, "coadd")) return -1;
+  if (k->ring_out) {
+    const long per_sec = SEG_PER_SEC, warm = (long) k->out_buf_sec * per_sec;
+    const long slot = k->done_segs < warm ? k->done_segs : k->done_segs % per_sec;
+    memcpy (k->out10 + (size_t) slot * k->out_bytes, seg, k->out_bytes);
+  }
+  k->done_segs++;
+  if (k->ring_out && k->done_segs % SEG_PER_SEC == 0) {
+    const long sec = k->done_segs / SEG_PER_SEC;
+    if (sec >= k->out_buf_sec) {
+      const size_t n = (size_t) (sec == k->out_buf_sec ? k->out_buf_sec : 1) * SEG_PER_SEC * k->out_bytes;
+      if (ring_sink_write (k->ring_out, k->out10, n, "outgoing")) return -1;
+    }
+  }
+  return 0;
+}
+
+static int ring_sink_write (vf_ring *r, const void *buf, size_t n, const char *what)
+{
+  if (vf_ring_get_nfull (r) == vf_ring_get_nbufs (r) - 1) {
+    fprintf (stderr, "failed buffer check\n");
+    logmsg ("ERR", "Only one free buffer left!  Aborting output.\n");
+    return -1;
+  }
+  const ssize_t w = vf_ring_write (r, buf, n);
+  if (w != (ssize_t) n) {
+    fprintf (stderr, "failed ipcio write\n");
+    logmsg ("ERR", "Tried to write %zu bytes to %s psrdada buffer but only wrote %zd.", n, what, w);
+    return -1;
+  }
+  return 0;
+}
+
 int main (int argc, char **argv)
 {
   const char *file = NULL, *datadir = ".", *logfile = NULL;
   int synth_n = 0, loops = 1, station = 1, nbuf = 0, write_fb = 1, single = 0, json = 0, rfi_flag = 0;
-  long shm_key = -1;
+  long shm_key = -1, key_out = 0, key_co = 0;                       /* :344-345 */
   unsigned long long seed = 102;
   vf_config cfg;
   vf_config_default (&cfg);
@@ -215,7 +267,9 @@ int main (int argc, char **argv)
         break;
       }
       case 'k': shm_key = (long) strtoul (optarg, NULL, 16); break;  /* input ring key, :541-569 */
-      case 'K': case 'C': case 'p': break;                        /* output ring keys / port of the reference: accepted, unused */
+      case 'K': key_out = (long) strtoul (optarg, NULL, 16); break;  /* heimdall ring, :377-383 */
+      case 'C': key_co = (long) strtoul (optarg, NULL, 16); break;   /* co-add ring, :370-376 */
+      case 'p': break;                                            /* port of the reference: accepted, unused */
       default: usage (); return 1;
     }
   }
@@ -255,6 +309,14 @@ int main (int argc, char **argv)
     if (vf_host_alloc (&ring_mem, (size_t) nbuf * SEC_BYTES)) { logmsg ("ERR", "cannot pin %d ring blocks\n", nbuf); return 21; }
     ring = vf_ring_create ((uint64_t) nbuf, SEC_BYTES, ring_mem);
   }
+  vf_ring *ring_out = NULL, *ring_co = NULL;
+  if (key_out && !(ring_out = vf_ring_connect_shm ((int) key_out))) {                 /* :550-558 */
+    logmsg ("ERR", "Unable to connect to outgoing PSRDADA buffer key=%lx!\n", key_out); return 1; }
+  if (key_co && !(ring_co = vf_ring_connect_shm ((int) key_co))) {                    /* :560-568 */
+    logmsg ("ERR", "Unable to connect to Coadding PSRDADA buffer key=%lx!\n", key_co); return 1; }
+  /* 10 s of main-stream output, flushed to the heimdall ring once full and second by second after that (:692-697) */
+  const int out_buf_sec = 10;
+  uint8_t *out10 = ring_out ? (uint8_t *) malloc ((size_t) out_buf_sec * SEG_PER_SEC * out_bytes) : NULL;
   uint8_t *obuf[2][2] = {{NULL, NULL}, {NULL, NULL}};             /* [slot][main, raw] pinned */
   for (int s = 0; s < 2; ++s)
     for (int k = 0; k < 2; ++k)
@@ -305,6 +367,7 @@ int main (int argc, char **argv)
     int first = 1, aborted = 0;
     int pend_slot[2] = {0, 0};
     int blocks_open = 0;
+    out_sinks sinks = { ring_out, ring_co, out10, out_bytes, 0, out_buf_sec };
     vf_reset_bandpass (h, -1);    /* the reference keeps the bandpass across observations (:700-709); a new
                                      stream here is a new antenna-time, so start clean */
 
@@ -336,9 +399,17 @@ int main (int argc, char **argv)
           if (!fb_main || (cfg.rfi_mode == 2 && !fb_raw)) { logmsg ("ERR", "cannot open output file in %s\n", datadir); exit_status = 1; aborted = 1; blocks_open++; break; }
           vf_write_sigproc_header (fb_main, &obs, vh, cfg.nbit, cfg.npol);
           if (fb_raw) vf_write_sigproc_header (fb_raw, &obs, vh, cfg.nbit, cfg.npol);
+        }
+        {
           char dh[VF_RING_HEADER_SIZE];
+          if (!write_fb) {
+            vf_fb_filename (fbfile, sizeof (fbfile), datadir, vh, obs.station_id, 0);
+            vf_fb_filename (fbfile_kur, sizeof (fbfile_kur), datadir, vh, obs.station_id, 1);
+          }
           vf_write_psrdada_header (dh, &obs, vh, cfg.nbit, cfg.npol, cfg.rfi_mode ? fbfile_kur : fbfile);
           logmsg ("INFO", "output header:\n%s", dh);
+          if (ring_out) vf_ring_header_write (ring_out, dh);                   /* :981-984 */
+          if (ring_co) vf_ring_header_write (ring_co, dh);                     /* :986-989 */
         }
         logmsg ("INFO", "Starting sec=%d, thread=%d\n", vf_vdif_frame_second (vh), vf_vdif_thread_id (vh));
         first = 0;
@@ -355,6 +426,7 @@ int main (int argc, char **argv)
           if (rc) { logmsg ("ERR", "segment failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; break; }
           if (fb_main) fwrite (obuf[slot][0], 1, out_bytes, fb_main);              /* :1438-1441 */
           if (fb_raw) fwrite (obuf[slot][1], 1, out_bytes, fb_raw);
+          if (sinks_segment (&sinks, obuf[slot][0])) { aborted = 1; exit_status = 1; break; }
         }
         if (cfg.inject_frb)
           vf_set_frb_injection (h, inject_now ? iseg * 1024 : -1, 80.f, (float) (2e-3 * 10 * 1024), 1.05f);   /* :1238-1240 */
@@ -390,6 +462,11 @@ int main (int argc, char **argv)
       if (rc) { logmsg ("ERR", "segment failed: %s\n", vf_last_error (h)); exit_status = 1; continue; }
       if (fb_main) fwrite (obuf[slot][0], 1, out_bytes, fb_main);
       if (fb_raw) fwrite (obuf[slot][1], 1, out_bytes, fb_raw);
+      if (!aborted && sinks_segment (&sinks, obuf[slot][0])) { aborted = 1; exit_status = 1; }
+    }
+    if (!first) {                                                 /* dada_hdu_unlock_write, :1498-1511 */
+      if (ring_out) vf_ring_end_of_data (ring_out);
+      if (ring_co) vf_ring_end_of_data (ring_co);
     }
     while (blocks_open > 0) { vf_ring_block_read_close (ring); blocks_open--; }
     if (!aborted) { uint64_t nb; while (vf_ring_block_read_open (ring, &nb)) vf_ring_block_read_close (ring); }   /* reach EOD */
@@ -412,6 +489,9 @@ int main (int argc, char **argv)
             total_data_s, total_segments, total_wall_s, total_wall_s > 0 ? total_data_s / total_wall_s : 0.0,
             cfg.nbit, cfg.npol, cfg.rfi_mode, total_data_s * (double) SEC_BYTES, exit_status | fa.rc);
   vf_mc_close (mc_sock);
+  if (ring_out) vf_ring_destroy (ring_out);
+  if (ring_co) vf_ring_destroy (ring_co);
+  free (out10);
   if (ring_registered) vf_host_unregister (vf_ring_data_base (ring));
   vf_ring_destroy (ring);
   for (int s = 0; s < 2; ++s) for (int k = 0; k < 2; ++k) vf_host_free (obuf[s][k]);
