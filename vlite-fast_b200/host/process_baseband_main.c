@@ -162,6 +162,9 @@ static void *feeder_synth (void *vp)
     unsigned char *blk = (unsigned char *) vf_ring_block_write_open (a->ring);
     if (!blk) return NULL;
     const uint32_t sec = a->second0 + (uint32_t) s;
+    /* 51 200 header words 5 KB apart: one cache miss each, so spread them over the cores or the
+     * feeder, not the GPU, sets the pace of the synthetic stream */
+#pragma omp parallel for schedule(static) num_threads(8)
     for (long f = 0; f < FRAMES_PER_SEC_2POL; ++f) {
       uint32_t *w0 = (uint32_t *) (blk + (size_t) f * VF_VD_FRM);
       *w0 = sec & 0x3FFFFFFFu;
