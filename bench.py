@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--npol", type=int, default=1)
     ap.add_argument("--rfi-mode", type=int, default=2)
     ap.add_argument("--k1-threads", type=int, default=0)
+    ap.add_argument("--max-batch", type=int, default=0, help="segments per launch pair (0 = library default, 1 = per segment)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-legacy", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -189,6 +190,7 @@ def main():
     n_ant = args.antennas
     p = pkg.Pipeline(ffts_per_seg=T, nbit=args.nbit, npol=args.npol, rfi_mode=args.rfi_mode, gpu_id=local,
                      n_antennas=n_ant, keep_power=1 if world > 1 else 0, k1_threads=args.k1_threads,
+                     max_batch_segments=args.max_batch,
                      power_segments=2 * SEG_PER_SEC if world > 1 else 0)
     out_bytes = p.out_bytes
 
@@ -265,7 +267,7 @@ def main():
             _, b, c = p.last_elapsed_ms()
             k1_ms += b; k2_ms += c
         p.set_serial(0)
-        k1_ms /= nser * SEG_PER_SEC; k2_ms /= nser * SEG_PER_SEC     # per launch
+        k1_ms /= nser * SEG_PER_SEC; k2_ms /= nser * SEG_PER_SEC     # per segment
         step_device(); p.sync()
 
     # ---- end to end through host buffers ----------------------------------------
@@ -307,22 +309,25 @@ def main():
     # ---- roofline of the dominant kernel -----------------------------------------
     peak, peak_src = peaks()
     nstream = 2 if args.rfi_mode == 2 else 1
-    alg_bytes_per_launch = n_ant * (2 * NSAMP + out_bytes * nstream)     # one segment
+    seg_per_launch = min(SEG_PER_SEC, args.max_batch if args.max_batch > 0 else 16)     # vf_process_device batches segments
+    alg_bytes_per_seg = n_ant * (2 * NSAMP + out_bytes * nstream)
+    alg_bytes_per_launch = alg_bytes_per_seg * seg_per_launch
     roofline = None
     if world == 1 and k1_ms > 0:
-        k1_avg_s = k1_ms / 1e3
+        k1_avg_s = k1_ms * seg_per_launch / 1e3                      # mean duration of one launch
         achieved = alg_bytes_per_launch / k1_avg_s / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch_1ant")
-                if traffic is not None:
-                    traffic = traffic * n_ant
+                tj = json.load(f)
+                traffic = tj.get("dram_bytes_per_launch_1ant")
+                if traffic is not None:     # the captured launch covered tj["segments_per_launch"] segments of 1 antenna
+                    traffic = traffic * n_ant * seg_per_launch / tj.get("segments_per_launch", 1)
         except Exception:
             pass
         # secondary view: the reference's arithmetic for this launch (real FFTs of both streams,
         # 2.5 N log2 N each) against the fp32 peak of the SMs at the clock measured above
-        alg_flops = n_ant * nstream * 2 * T * 2.5 * 12500 * np.log2(12500)
+        alg_flops = seg_per_launch * n_ant * nstream * 2 * T * 2.5 * 12500 * np.log2(12500)
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         fp32 = {"alg_flops_per_launch": alg_flops, "achieved_tflops": alg_flops / k1_avg_s / 1e12, "peak_tflops": fp32_peak,
@@ -332,10 +337,11 @@ def main():
         roofline = {"bound": "hbm", "kernel": "vf_k1_pipelined" if args.k1_threads == 0 else "vf_k1_channelise<%d>" % args.k1_threads,
                     "fp32": fp32, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "alg_bytes_per_launch": alg_bytes_per_launch,
-                    "k1_ms_per_launch": k1_ms, "k2_ms_per_launch": k2_ms,
+                    "alg_bytes_per_launch": alg_bytes_per_launch, "segments_per_launch": seg_per_launch,
+                    "k1_ms_per_launch": k1_ms * seg_per_launch, "k2_ms_per_launch": k2_ms * seg_per_launch,
+                    "k1_ms_per_segment": k1_ms, "k2_ms_per_segment": k2_ms,
                     "launch_timing": "CUDA events around each launch on the library's stream, segments serialised (vf_set_serial) so that no queueing is included",
-                    "whole_chain_achieved": alg_bytes_per_launch * SEG_PER_SEC * args.steps / (t_ms / 1e3) / 1e9}
+                    "whole_chain_achieved": alg_bytes_per_seg * SEG_PER_SEC * args.steps / (t_ms / 1e3) / 1e9}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -369,7 +375,7 @@ def main():
                    "timing": "CUDA events on the library's stream (fork/join over its 2 slot streams)" if world == 1
                              else "wall clock between barrier+synchronize, max over ranks"},
         "clocks": clocks, "e2e": e2e,
-        "gpu_launches": int(args.steps * SEG_PER_SEC * 2 + (args.steps * SEG_PER_SEC * n_ant if world > 1 else 0)),
+        "gpu_launches": int(args.steps * -(-SEG_PER_SEC // seg_per_launch) * 2 + (args.steps * SEG_PER_SEC * n_ant if world > 1 else 0)),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "legacy_cuda": legacy,
         "wall_ms_per_step": 1e3 * wall / args.steps,
     }

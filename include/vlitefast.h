@@ -68,7 +68,9 @@ typedef struct vf_config {
                                  channeliser with that many threads (A/B comparison)          */
   int power_segments;  /* 0      f32 tiles kept for this many consecutive segments (0 = 1): lets
                                  vf_coadd_batch reduce a whole second in one collective       */
-  int reserved[6];
+  int max_batch_segments;/* 0    vf_process_device: consecutive segments per launch pair (0 = up to 16, 1 = one
+                                 launch pair per segment); statistics dumps, histogram and FRB injection imply 1 */
+  int reserved[5];
 } vf_config;
 
 typedef struct vf_handle vf_handle;

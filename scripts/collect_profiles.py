@@ -57,7 +57,8 @@ for line in k1.splitlines():
     if line.startswith("dram__bytes_write.sum"): wr = float(f[1]) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}[f[2]]
 json.dump({"source": "profiles/%s_k1_final_ncu_summary.txt (ncu --set full, one launch, 1 antenna, rfi_mode 2)" % tag,
            "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch_1ant": rd + wr,
+           "segments_per_launch": last_json(os.path.join(G, "bench_1ant.log"))["roofline"]["segments_per_launch"],
            "note": "the power tiles written by the launch are still dirty in the 126 MB L2 when the kernel ends (the normaliser reads "
-                   "them from there and from DRAM), so most of them are not in the write count; algorithmic bytes per launch are 25 862 144",
+                   "them from there and from DRAM), so most of them are not in the write count; algorithmic bytes are 25 862 144 per segment",
            "launch_shares": shares}, open(os.path.join(P, "k1_traffic.json"), "w"), indent=1)
 print(json.dumps(shares, indent=1))

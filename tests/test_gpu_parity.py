@@ -182,6 +182,35 @@ def test_device_resident_equals_host(pkg):
             assert np.array_equal(m[s, a], want[s][0][a]) and np.array_equal(r[s, a], want[s][1][a])
 
 
+def test_batched_launches_equal_per_segment(pkg):
+    """vf_process_device covers consecutive segments with one launch pair (max_batch_segments): same bytes, masks
+    and detected power of the last segment as one launch pair per segment, for whole and ragged batches"""
+    import torch
+    T, nseg, n = 256, 5, 2
+    data = np.empty((nseg, n, 2, T * 12500), np.uint8)
+    for s in range(nseg):
+        for a in range(n):
+            data[s, a, 0], data[s, a, 1] = make_input(pkg, T, seed=51, antenna=a, sample0=s * T * 12500, **RFI)
+    d_in = torch.from_numpy(data).cuda()
+    res = []
+    for mb in (1, 0, 2):
+        with pkg.Pipeline(ffts_per_seg=T, nbit=4, npol=2, rfi_mode=2, n_antennas=n, max_batch_segments=mb, keep_power=1) as p:
+            d_main = torch.zeros((nseg, n, p.out_bytes), dtype=torch.uint8, device="cuda")
+            d_raw = torch.zeros_like(d_main)
+            for _ in range(2):          # twice: the second pass starts from a settled bandpass
+                p.process_device(n, nseg, d_in.data_ptr(), d_main.data_ptr(), d_raw.data_ptr())
+            p.sync()
+            res.append((d_main.cpu().numpy(), d_raw.cpu().numpy(), [p.get_mask(a) for a in range(n)],
+                        [p.get_detected_power(a, 0) for a in range(n)], [p.get_power_f32(a, 0) for a in range(n)],
+                        [p.get_bandpass(a, 0) for a in range(n)]))
+    for r in res[1:]:
+        assert np.array_equal(res[0][0], r[0]) and np.array_equal(res[0][1], r[1])
+        for a in range(n):
+            assert np.array_equal(res[0][2][a], r[2][a])
+            assert np.array_equal(res[0][3][a], r[3][a]) and np.array_equal(res[0][4][a], r[4][a])
+            assert np.array_equal(res[0][5][a], r[5][a])
+
+
 def test_k1_thread_variants_agree(pkg):
     """the pipelined channeliser (0, the default) and the monolithic one at three CTA sizes give the same bits;
     T = 1024 x 2 antennas makes every CTA of the pipelined kernel draw many items from the shared counter"""

@@ -28,7 +28,7 @@ class VfConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "abi_version", "nfft", "nscrunch", "ffts_per_seg", "nkurto", "chanmin", "chanmax", "nbit",
         "npol", "rfi_mode", "do_histo", "keep_stats", "keep_power", "inject_frb", "gpu_id",
-        "n_antennas", "k1_threads", "power_segments")] + [("reserved", C.c_int * 6)]
+        "n_antennas", "k1_threads", "power_segments", "max_batch_segments")] + [("reserved", C.c_int * 5)]
 
 
 def _load(name):

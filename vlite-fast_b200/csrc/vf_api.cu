@@ -66,6 +66,8 @@ struct vf_handle {
   cudaStream_t ctl;
   cudaStream_t coadd_st;      /* co-add runs beside the next segments, not in front of them */
   vf_slot slot[2];
+  int batch_cap;              /* consecutive segments the tile / weight / mask buffers of a slot hold */
+  int last_batch, last_n_ant; /* segments / antennas of the last launch (the getters look at its last segment) */
   int next_slot;              /* slot of the next synchronous segment */
   int last_slot;              /* slot that holds the last processed segment */
   cudaEvent_t ev_k2_last;     /* completion of the most recent K2 */
@@ -161,18 +163,30 @@ static void vf_dag_constants (int nsamp, double out[5])
   out[4] = sqrt (2. / (mu2 * (A - 4)));
 }
 
-static int vf_alloc_slot (vf_handle *h, vf_slot *s)
+/* tile, weight and mask buffers of a slot for nb consecutive segments of n_antennas antennas */
+static int vf_alloc_tiles (vf_handle *h, vf_slot *s, int nb)
 {
-  const size_t na = (size_t) h->n_ant;
+  const size_t na = (size_t) h->n_ant * nb;
   const int mode = h->cfg.rfi_mode;
-  CK (cudaStreamCreateWithFlags (&s->st, cudaStreamNonBlocking));
-  CK (cudaMalloc ((void **) &s->d_in, na * 2 * h->nsamp));
+  cudaFree (s->P_raw); cudaFree (s->P_kur); cudaFree (s->w); cudaFree (s->mask);
+  s->P_raw = s->P_kur = NULL; s->w = NULL; s->mask = NULL;
   if (mode != 1) CK (cudaMalloc ((void **) &s->P_raw, na * h->tile_elems * sizeof (float2)));
   if (mode != 0) CK (cudaMalloc ((void **) &s->P_kur, na * h->tile_elems * sizeof (float2)));
   CK (cudaMalloc ((void **) &s->w, na * h->T * sizeof (float)));
   CK (cudaMalloc ((void **) &s->mask, na * h->T * sizeof (uint32_t)));
   CK (cudaMemset (s->w, 0, na * h->T * sizeof (float)));
   CK (cudaMemset (s->mask, 0, na * h->T * sizeof (uint32_t)));
+  return VF_OK;
+}
+
+static int vf_alloc_slot (vf_handle *h, vf_slot *s)
+{
+  const size_t na = (size_t) h->n_ant;
+  const int mode = h->cfg.rfi_mode;
+  CK (cudaStreamCreateWithFlags (&s->st, cudaStreamNonBlocking));
+  CK (cudaMalloc ((void **) &s->d_in, na * 2 * h->nsamp));
+  int rc = vf_alloc_tiles (h, s, 1);
+  if (rc) return rc;
   CK (cudaMalloc ((void **) &s->d_work, sizeof (unsigned int)));
   CK (cudaMemset (s->d_work, 0, sizeof (unsigned int)));
   s->work_base = 0;
@@ -180,6 +194,34 @@ static int vf_alloc_slot (vf_handle *h, vf_slot *s)
   if (mode == 2) CK (cudaMalloc ((void **) &s->d_out_raw, na * h->out_bytes));
   CK (cudaEventCreateWithFlags (&s->ev_k2, cudaEventDisableTiming));
   CK (cudaEventCreateWithFlags (&s->ev_done, cudaEventDisableTiming));
+  return VF_OK;
+}
+
+/* segments that one launch pair may cover (vf_process_device): the statistics dumps, the histogram
+ * and the FRB injection are per segment, so they keep launches per segment */
+/* index of (last segment of the last launch, antenna) in the slot's weight / mask / tile buffers */
+static size_t vf_last_index (const vf_handle *h, int antenna)
+{
+  return (size_t) (h->last_batch - 1) * h->last_n_ant + antenna;
+}
+
+static int vf_max_batch (const vf_handle *h)
+{
+  const vf_config &c = h->cfg;
+  if (c.keep_stats || c.do_histo || c.inject_frb) return 1;
+  const int m = c.max_batch_segments > 0 ? c.max_batch_segments : 16;
+  return m;
+}
+
+static int vf_ensure_batch (vf_handle *h, int nb)
+{
+  if (nb <= h->batch_cap) return VF_OK;
+  CK (cudaDeviceSynchronize ());
+  for (int i = 0; i < 2; ++i) {
+    int rc = vf_alloc_tiles (h, &h->slot[i], nb);
+    if (rc) return rc;
+  }
+  h->batch_cap = nb;
   return VF_OK;
 }
 
@@ -231,6 +273,7 @@ int vf_create (const vf_config *cfg, vf_handle **out)
   if (!(cfg->npol == 1 || cfg->npol == 2)) return VF_ERR_ARG;
   if (cfg->rfi_mode < 0 || cfg->rfi_mode > 2) return VF_ERR_ARG;
   if (cfg->n_antennas < 1 || cfg->n_antennas > 4096) return VF_ERR_ARG;
+  if (cfg->max_batch_segments < 0 || cfg->max_batch_segments > 64) return VF_ERR_ARG;
   if (!(cfg->k1_threads == 0 || cfg->k1_threads == 320 || cfg->k1_threads == 512 || cfg->k1_threads == 640)) return VF_ERR_ARG;
 
   int ndev = 0;
@@ -242,6 +285,7 @@ int vf_create (const vf_config *cfg, vf_handle **out)
   h->cfg = *cfg;
   *out = h;    /* handed back even on failure so that vf_last_error works; caller destroys */
   h->T = cfg->ffts_per_seg;
+  h->batch_cap = 1; h->last_batch = 1; h->last_n_ant = 1;
   h->ntime = h->T / VF_NSCRUNCH;
   h->n_ant = cfg->n_antennas;
   h->nsamp = (size_t) h->T * VF_NFFT;
@@ -364,15 +408,16 @@ int vf_host_unregister (void *p)
  * d_in: [n_ant][2][T*12500] on the device.  Outputs to d_main / d_raw
  * ([n_ant][out_bytes]).  timed >= 0: record the K1/K2 events of that index. */
 static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_t *d_in,
-                               uint8_t *d_main, uint8_t *d_raw, int timed)
+                               uint8_t *d_main, uint8_t *d_raw, int timed, int n_seg = 1)
 {
+  if (n_seg > h->batch_cap) return vf_fail (h, VF_ERR_STATE, "batch of %d segments, buffers hold %d", n_seg, h->batch_cap);
   const vf_config &c = h->cfg;
   vf_k1_params k1;
   memset (&k1, 0, sizeof (k1));
   k1.in = d_in;
   k1.pol_stride = h->nsamp;
   k1.ant_stride = 2 * h->nsamp;
-  k1.T = h->T; k1.n_ant = n_ant; k1.rfi_mode = c.rfi_mode;
+  k1.T = h->T; k1.n_ant = n_ant * n_seg; k1.rfi_mode = c.rfi_mode;   /* (segment, antenna) pairs are the channeliser's antennas */
   k1.P_raw = s->P_raw; k1.P_kur = s->P_kur;
   k1.w = s->w; k1.mask = s->mask;
   k1.pw = h->pw; k1.kur = h->kur; k1.dag = h->dag;
@@ -388,7 +433,7 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
     k1.frb_width = h->frb_width; k1.frb_amp = h->frb_amp;
   }
   if (h->histo) CK (cudaMemsetAsync (h->histo, 0, (size_t) n_ant * 512 * sizeof (unsigned int), s->st));
-  const int n_items = n_ant * h->T;
+  const int n_items = n_ant * n_seg * h->T;
   const int grid = n_items < h->nsm ? n_items : h->nsm;
   const int threads = c.k1_threads;            /* 0: pipelined kernel; 320/512/640: monolithic kernel (A/B) */
   if (threads == 0) {
@@ -406,8 +451,8 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
   if (h->have_k2_last) CK (cudaStreamWaitEvent (s->st, h->ev_k2_last, 0));
   /* this segment overwrites the tile of segment (seg_counter - ave_nseg): wait for a co-add that still reads it */
   for (int b = 0; b < 2; ++b) {
-    const long victim = h->seg_counter - h->ave_nseg;
-    if (h->coadd_batch[b].pending && victim >= h->coadd_batch[b].lo && victim < h->coadd_batch[b].hi) {
+    const long victim_lo = h->seg_counter - h->ave_nseg, victim_hi = victim_lo + n_seg;    /* [lo, hi) */
+    if (h->coadd_batch[b].pending && victim_lo < h->coadd_batch[b].hi && victim_hi > h->coadd_batch[b].lo) {
       CK (cudaStreamWaitEvent (s->st, h->coadd_batch[b].ev, 0));
       h->coadd_batch[b].pending = 0;
     }
@@ -416,18 +461,18 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
   memset (&k2, 0, sizeof (k2));
   k2.P_raw = s->P_raw; k2.P_kur = s->P_kur; k2.w = s->w; k2.mask = s->mask;
   k2.bp_raw = h->bp_raw; k2.bp_kur = (c.rfi_mode == 2) ? h->bp_kur : h->bp_raw;
-  k2.T = h->T; k2.n_ant = n_ant; k2.rfi_mode = c.rfi_mode; k2.npol = c.npol; k2.nbit = c.nbit;
+  k2.T = h->T; k2.n_ant = n_ant; k2.n_seg = n_seg; k2.rfi_mode = c.rfi_mode; k2.npol = c.npol; k2.nbit = c.nbit;
   /* bp_scale = float(tsamp/tsmooth), src/process_baseband.cu:737-741 */
   k2.bp_scale = (float) (((double) VF_NFFT / 128000000 * VF_NSCRUNCH) / 1.0);
   k2.out_main = d_main; k2.out_raw = d_raw; k2.out_stride = h->out_bytes;
   { static const char *dbg = getenv ("VF_K2_DEBUG"); k2.debug = dbg ? atoi (dbg) : 0; }
   {
-    /* tile slot of this segment in the ring of kept tiles (sized for the handle's n_antennas) */
-    const size_t tile_all = (size_t) h->n_ant * c.npol * h->ntime * VF_NCHANOUT;
-    const size_t off = (size_t) (h->seg_counter % h->ave_nseg) * tile_all;
-    k2.ave_main = h->ave_main ? h->ave_main + off : NULL;
-    k2.ave_raw = h->ave_raw ? h->ave_raw + off : NULL;
-    h->seg_counter++;
+    /* tile slots of these segments in the ring of kept tiles (sized for the handle's n_antennas) */
+    k2.ave_main = h->ave_main; k2.ave_raw = h->ave_raw;
+    k2.ave_seg0 = h->seg_counter; k2.ave_nseg = h->ave_nseg;
+    k2.ave_seg_elems = (size_t) h->n_ant * c.npol * h->ntime * VF_NCHANOUT;
+    h->seg_counter += n_seg;
+    h->last_batch = n_seg; h->last_n_ant = n_ant;
   }
   CK (vf_launch_k2 (k2, s->st));
   if (h->debug_sync) CK (cudaStreamSynchronize (s->st));
@@ -619,13 +664,20 @@ int vf_process_device (vf_handle *h, int n_ant, int n_seg, const uint8_t *d_in,
   if (h->cfg.rfi_mode == 2 && !d_fb_raw) return vf_fail (h, VF_ERR_ARG, "rfi_mode 2 needs d_fb_raw");
   if (h->slot[0].pending || h->slot[1].pending) return vf_fail (h, VF_ERR_STATE, "asynchronous segment in flight");
   CK (cudaSetDevice (h->cfg.gpu_id));
-  int rc = vf_timing_begin (h, n_seg);
-  if (rc) return rc;
   const size_t in_seg = (size_t) n_ant * 2 * h->nsamp, out_seg = (size_t) n_ant * h->out_bytes;
-  for (int sg = 0; sg < n_seg; ++sg) {
+  /* consecutive segments share a launch pair: the channeliser takes (segment, antenna) pairs as its
+   * antennas, the normaliser walks the segments in time order inside the kernel.  Fewer, longer
+   * launches: less start-up and tail per segment (cfg.max_batch_segments) */
+  const int nb = n_seg < vf_max_batch (h) ? n_seg : vf_max_batch (h);
+  int rc = vf_ensure_batch (h, nb);
+  if (rc) return rc;
+  rc = vf_timing_begin (h, (n_seg + nb - 1) / nb);       /* one (K1, K2) pair of events per launch pair */
+  if (rc) return rc;
+  for (int sg = 0, bi = 0; sg < n_seg; sg += nb, ++bi) {
+    const int m = n_seg - sg < nb ? n_seg - sg : nb;
     vf_slot *s = &h->slot[h->next_slot];
     rc = vf_enqueue_segment (h, s, n_ant, d_in + (size_t) sg * in_seg, d_fb_main + (size_t) sg * out_seg,
-                             d_fb_raw ? d_fb_raw + (size_t) sg * out_seg : NULL, sg < h->n_timed ? sg : -1);
+                             d_fb_raw ? d_fb_raw + (size_t) sg * out_seg : NULL, bi < h->n_timed ? bi : -1, m);
     if (rc) return rc;
     h->last_slot = h->next_slot;
     h->next_slot ^= 1;
@@ -718,7 +770,7 @@ int vf_get_stats (vf_handle *h, int antenna, float *pw, float *kur, float *dag,
   if (weights) {
     if (!h->cfg.rfi_mode) return vf_fail (h, VF_ERR_STATE, "weights need rfi_mode != 0");
     /* both pols always carry the same weight (src/pb_kernels.cu:132) */
-    CK (cudaMemcpy (weights, h->slot[h->last_slot].w + (size_t) antenna * T, T * 4, cudaMemcpyDeviceToHost));
+    CK (cudaMemcpy (weights, h->slot[h->last_slot].w + vf_last_index (h, antenna) * T, T * 4, cudaMemcpyDeviceToHost));
     memcpy (weights + T, weights, T * 4);
   }
   if (histo) {
@@ -735,7 +787,7 @@ int vf_get_mask (vf_handle *h, int antenna, uint32_t *mask)
   if (!mask) return VF_ERR_ARG;
   rc = vf_sync (h);
   if (rc) return rc;
-  CK (cudaMemcpy (mask, h->slot[h->last_slot].mask + (size_t) antenna * h->T, (size_t) h->T * 4, cudaMemcpyDeviceToHost));
+  CK (cudaMemcpy (mask, h->slot[h->last_slot].mask + vf_last_index (h, antenna) * h->T, (size_t) h->T * 4, cudaMemcpyDeviceToHost));
   return VF_OK;
 }
 
@@ -764,7 +816,7 @@ int vf_get_detected_power (vf_handle *h, int antenna, int which, float *out)
   rc = vf_sync (h);
   if (rc) return rc;
   vf_slot *s = &h->slot[h->last_slot];
-  const size_t n = h->tile_elems, off = (size_t) antenna * n;
+  const size_t n = h->tile_elems, off = vf_last_index (h, antenna) * n;
   const bool want_kur = (which == 0 && mode != 0);
   /* the device tile is blocked ([4096/16][T][16], VF_PBLK): copy it out and put it in [T][4096] order */
   std::vector<float2> blk (n), blk_raw;
@@ -774,7 +826,7 @@ int vf_get_detected_power (vf_handle *h, int antenna, int which, float *out)
     /* time steps with an empty mask were not re-transformed: identical to raw */
     mk.resize (h->T);
     blk_raw.resize (n);
-    CK (cudaMemcpy (mk.data (), s->mask + (size_t) antenna * h->T, (size_t) h->T * 4, cudaMemcpyDeviceToHost));
+    CK (cudaMemcpy (mk.data (), s->mask + vf_last_index (h, antenna) * h->T, (size_t) h->T * 4, cudaMemcpyDeviceToHost));
     CK (cudaMemcpy (blk_raw.data (), s->P_raw + off, n * sizeof (float2), cudaMemcpyDeviceToHost));
   }
   float2 *o2 = reinterpret_cast<float2 *> (out);

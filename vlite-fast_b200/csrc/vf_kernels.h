@@ -57,10 +57,12 @@ struct vf_k2_params {
   const uint32_t *mask;
   float2 *bp_raw, *bp_kur;    /* [n_ant][4096] running bandpass (pol0, pol1) */
   int T, n_ant, rfi_mode, npol, nbit;
+  int n_seg;                  /* consecutive segments in this launch: data of (seg, ant) at index seg * n_ant + ant */
   float bp_scale;
   uint8_t *out_main, *out_raw;/* [n_ant][out_bytes] */
   size_t out_stride;
-  float *ave_main, *ave_raw;  /* optional [n_ant][npol][T/8][4096] */
+  float *ave_main, *ave_raw;  /* optional ring of ave_nseg tiles [n_ant][npol][T/8][4096]; segment seg of the launch goes */
+  long ave_seg0; int ave_nseg; size_t ave_seg_elems;   /* to tile (ave_seg0 + seg) % ave_nseg, ave_seg_elems floats apart */
   int debug;                  /* VF_K2_DEBUG (profiling only): 1 skip fan-out, 2 skip recursion, 4 skip weight division */
 };
 
