@@ -10,8 +10,9 @@ PKG      := vlite-fast_b200
 CSRC     := $(PKG)/csrc
 HOST     := $(PKG)/host
 LIB      := $(PKG)/libvlitefast.so
+GENLIB   := $(PKG)/libvlitegen.so
 
-all: $(LIB) host oracle build/vf_fft_hosttest
+all: $(LIB) $(GENLIB) host oracle build/vf_fft_hosttest
 
 build:
 	mkdir -p build
@@ -25,17 +26,21 @@ build/vf_api.o: $(CSRC)/vf_api.cu $(CSRC)/vf_kernels.h include/vlitefast.h | bui
 $(LIB): build/vf_kernels.o build/vf_api.o
 	$(NVCC) -shared $(GENCODE) -o $@ $^ -ldl
 
+# GPU baseband generator: its own library, the only one that links cuFFT
+$(GENLIB): $(CSRC)/vf_genbase_gpu.cu include/vlitegen.h | build
+	$(NVCC) $(NVFLAGS) -shared -o $@ $< -lcufft
+
 build/vf_fft_hosttest: $(CSRC)/vf_fft_hosttest.cu $(CSRC)/vf_fft12500.cuh | build
 	$(NVCC) -O2 -std=c++17 -I$(CSRC) -o $@ $<
 
-host: $(LIB)
+host: $(LIB) $(GENLIB)
 	@if [ -f $(HOST)/Makefile ]; then $(MAKE) -C $(HOST) HOSTCC=$(HOSTCC); fi
 
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(GENLIB)
 	$(MAKE) -C oracle clean
 
 .PHONY: all host oracle clean

@@ -182,6 +182,31 @@ def test_device_resident_equals_host(pkg):
             assert np.array_equal(m[s, a], want[s][0][a]) and np.array_equal(r[s, a], want[s][1][a])
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pipelined_channeliser_stress(pkg, mode):
+    """the two warp groups of the pipelined channeliser hand buffers over through named barriers and mbarriers:
+    odd item counts, more or fewer items than CTAs, every RFI mode, dropped frames, repeated launches -- always the
+    bits of the monolithic kernel"""
+    gen = dict(drop_period=9, drop_len=1, drop_pol_skew=2, **RFI)
+    for T, n in ((8, 1), (40, 3), (136, 2), (152, 1)):
+        ins = [make_input(pkg, T, seed=90 + T, antenna=a, **gen) for a in range(n)]
+        outs = []
+        for nt in (640, 0):
+            with pkg.Pipeline(ffts_per_seg=T, nbit=8, npol=2, rfi_mode=mode, n_antennas=n, k1_threads=nt) as p:
+                runs = []
+                for _ in range(3):
+                    m, r = p.process_batch([i[0] for i in ins], [i[1] for i in ins])
+                    runs.append((m, r, [p.get_mask(a) for a in range(n)] if mode else None))
+                outs.append(runs)
+        for a_run, b_run in zip(*outs):
+            for a in range(n):
+                assert np.array_equal(a_run[0][a], b_run[0][a])
+                if mode == 2:
+                    assert np.array_equal(a_run[1][a], b_run[1][a])
+                if mode:
+                    assert np.array_equal(a_run[2][a], b_run[2][a])
+
+
 def test_batched_launches_equal_per_segment(pkg):
     """vf_process_device covers consecutive segments with one launch pair (max_batch_segments): same bytes, masks
     and detected power of the last segment as one launch pair per segment, for whole and ragged batches"""

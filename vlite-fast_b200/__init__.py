@@ -13,8 +13,8 @@ is loaded through ``__graft_entry__.load_package()`` under the module name
 from .sharding import antennas_of_rank, coadd_scale
 from .binding import (VfConfig, Pipeline, VfError, lib, hostlib, GenParams, gen_samples,
                       gen_vdif_second, NFFT, NCHANOUT, NSCRUNCH, NSUB, VD_FRM, VD_DAT,
-                      FRAMES_PER_SEC)
+                      FRAMES_PER_SEC, VfgConfig, GpuGenerator, genlib)
 
 __all__ = ["VfConfig", "Pipeline", "VfError", "lib", "hostlib", "GenParams", "gen_samples",
            "gen_vdif_second", "NFFT", "NCHANOUT", "NSCRUNCH", "NSUB", "VD_FRM", "VD_DAT",
-           "FRAMES_PER_SEC"]
+           "FRAMES_PER_SEC", "VfgConfig", "GpuGenerator", "genlib"]

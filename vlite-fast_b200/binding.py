@@ -328,3 +328,85 @@ class Pipeline:
         sm = np.empty((self.cfg.npol, self.ntime, NCHANOUT), np.float32) if want else None
         self._ck(self.L.vf_coadd_segment(self.h, root, total_antennas, _ptr(fb), _ptr(sm)))
         return fb, sm
+
+
+# ---- libvlitegen.so: GPU baseband generator (include/vlitegen.h) -------------
+class VfgConfig(C.Structure):
+    _fields_ = [("dm", C.c_double), ("pulse_period", C.c_double), ("ampl", C.c_float * 2), ("skip_period", C.c_int),
+                ("add_rfi", C.c_int), ("seed", C.c_ulonglong), ("buflen", C.c_longlong), ("gpu_id", C.c_int),
+                ("reserved", C.c_int * 7)]
+
+
+_genlib = None
+
+
+def genlib():
+    global _genlib
+    if _genlib is not None:
+        return _genlib
+    L = _load("libvlitegen.so")
+    vp = C.c_void_p
+    L.vfg_config_default.argtypes = [C.POINTER(VfgConfig)]
+    L.vfg_create.argtypes = [C.POINTER(VfgConfig), C.POINTER(vp)]
+    L.vfg_destroy.argtypes = [vp]
+    L.vfg_last_error.argtypes = [vp]; L.vfg_last_error.restype = C.c_char_p
+    L.vfg_block_samples.argtypes = [vp]; L.vfg_block_samples.restype = C.c_longlong
+    L.vfg_sweep_samples.argtypes = [vp]; L.vfg_sweep_samples.restype = C.c_longlong
+    L.vfg_generate.argtypes = [vp, vp, vp, C.c_size_t]
+    L.vfg_last_block_f32.argtypes = [vp, C.c_int, vp]
+    L.vfg_generate_vdif_second.argtypes = [vp, C.c_int, C.c_uint32, vp]
+    _genlib = L
+    return L
+
+
+class GpuGenerator:
+    """vfg_* handle: coherent-dispersion baseband generator on the GPU."""
+
+    def __init__(self, **kw):
+        self.L = genlib()
+        self.cfg = VfgConfig()
+        self.L.vfg_config_default(C.byref(self.cfg))
+        for k, v in kw.items():
+            if k == "ampl":
+                self.cfg.ampl[0], self.cfg.ampl[1] = v
+            else:
+                setattr(self.cfg, k, v)
+        self.h = C.c_void_p()
+        rc = self.L.vfg_create(C.byref(self.cfg), C.byref(self.h))
+        if rc:
+            msg = self.L.vfg_last_error(self.h).decode() if self.h else "no CUDA device"
+            self.L.vfg_destroy(self.h)
+            self.h = None
+            raise VfError(rc, msg)
+        self.block_samples = self.L.vfg_block_samples(self.h)
+        self.sweep_samples = self.L.vfg_sweep_samples(self.h)
+
+    def _ck(self, rc):
+        if rc:
+            raise VfError(rc, self.L.vfg_last_error(self.h).decode())
+
+    def generate(self, n):
+        p0, p1 = np.empty(n, np.uint8), np.empty(n, np.uint8)
+        self._ck(self.L.vfg_generate(self.h, p0.ctypes.data, p1.ctypes.data, n))
+        return p0, p1
+
+    def last_block_f32(self, pol):
+        out = np.empty(self.block_samples, np.float32)
+        self._ck(self.L.vfg_last_block_f32(self.h, pol, out.ctypes.data))
+        return out
+
+    def vdif_second(self, station, second):
+        out = np.empty(FRAMES_PER_SEC * 2 * VD_FRM, np.uint8)
+        self._ck(self.L.vfg_generate_vdif_second(self.h, station, second, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.vfg_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
