@@ -15,11 +15,12 @@ def last_json(path):
 
 
 for src, dst in (("bench_1ant.log", "bench_1ant"), ("bench_8ant.log", "bench_8ant"), ("bench_ref.log", "bench_ref"),
-                 ("bench_1ant_mono.log", "bench_1ant_monolithic_k1"), ("exe_60s.log", "exe_60s")):
+                 ("bench_1ant_mono.log", "bench_1ant_monolithic_k1"), ("bench_1ant_nobatch.log", "bench_1ant_launch_per_segment"),
+                 ("exe_60s.log", "exe_60s")):
     p = os.path.join(G, src)
     if os.path.exists(p):
         json.dump(last_json(p), open(os.path.join(P, "%s_%s.json" % (tag, dst)), "w"), indent=1)
-for src, dst in (("launches.csv", "launches_final.csv"), ("fp32_rate.log", "fp32_rate_ubench.txt")):
+for src, dst in (("launches.csv", "launches_final.csv"), ("fp32_rate.log", "fp32_rate_ubench.txt"), ("h2d_rate.log", "h2d_rate_ubench.txt")):
     if os.path.exists(os.path.join(G, src)):
         shutil.copy(os.path.join(G, src), os.path.join(P, "%s_%s" % (tag, dst)))
 
@@ -58,7 +59,7 @@ for line in k1.splitlines():
 json.dump({"source": "profiles/%s_k1_final_ncu_summary.txt (ncu --set full, one launch, 1 antenna, rfi_mode 2)" % tag,
            "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch_1ant": rd + wr,
            "segments_per_launch": last_json(os.path.join(G, "bench_1ant.log"))["roofline"]["segments_per_launch"],
-           "note": "the power tiles written by the launch are still dirty in the 126 MB L2 when the kernel ends (the normaliser reads "
-                   "them from there and from DRAM), so most of them are not in the write count; algorithmic bytes are 25 862 144 per segment",
+           "note": "reads = the input samples, once; writes = the detected-power tiles between the two kernels (42 MB per segment on this workload), which a "
+                   "launch over several segments no longer keeps in the 126 MB L2; they are not algorithmic bytes (25 862 144 per segment: samples in, packed filterbank out)",
            "launch_shares": shares}, open(os.path.join(P, "k1_traffic.json"), "w"), indent=1)
 print(json.dumps(shares, indent=1))
