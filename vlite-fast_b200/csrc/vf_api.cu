@@ -209,7 +209,11 @@ static int vf_max_batch (const vf_handle *h)
 {
   const vf_config &c = h->cfg;
   if (c.keep_stats || c.do_histo || c.inject_frb) return 1;
-  const int m = c.max_batch_segments > 0 ? c.max_batch_segments : 16;
+  int m = c.max_batch_segments > 0 ? c.max_batch_segments : 16;
+  /* the tiles of a batch live in both slots: keep them under ~24 GB per slot */
+  const size_t per_seg = (size_t) h->n_ant * h->tile_elems * sizeof (float2) * (c.rfi_mode == 2 ? 2 : 1);
+  const size_t cap = ((size_t) 24 << 30) / (per_seg ? per_seg : 1);
+  if ((size_t) m > cap) m = cap ? (int) cap : 1;
   return m;
 }
 
