@@ -164,12 +164,15 @@ def main():
     ap.add_argument("--rfi-mode", type=int, default=2)
     ap.add_argument("--k1-threads", type=int, default=0)
     ap.add_argument("--max-batch", type=int, default=0, help="segments per launch pair (0 = library default, 1 = per segment)")
+    ap.add_argument("--clean", action="store_true", help="no impulsive RFI in the synthetic input (no time step needs the second FFT)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-legacy", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    if args.clean:
+        GEN["rfi_amp"] = 0
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
