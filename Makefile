@@ -12,7 +12,7 @@ HOST     := $(PKG)/host
 LIB      := $(PKG)/libvlitefast.so
 GENLIB   := $(PKG)/libvlitegen.so
 
-all: $(LIB) $(GENLIB) host oracle build/vf_fft_hosttest
+all: $(LIB) $(GENLIB) host oracle build/vf_fft_hosttest scripts/ubench/fp32_rate
 
 build:
 	mkdir -p build
@@ -29,6 +29,10 @@ $(LIB): build/vf_kernels.o build/vf_api.o
 # GPU baseband generator: its own library, the only one that links cuFFT
 $(GENLIB): $(CSRC)/vf_genbase_gpu.cu include/vlitegen.h | build
 	$(NVCC) $(NVFLAGS) -shared -o $@ $< -lcufft
+
+# issue-rate microbenchmark of the packed fp32 instructions
+scripts/ubench/fp32_rate: scripts/ubench/fp32_rate.cu
+	$(NVCC) -O3 $(GENCODE) -o $@ $<
 
 build/vf_fft_hosttest: $(CSRC)/vf_fft_hosttest.cu $(CSRC)/vf_fft12500.cuh | build
 	$(NVCC) -O2 -std=c++17 -I$(CSRC) -o $@ $<
