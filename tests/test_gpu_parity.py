@@ -313,6 +313,32 @@ def test_coadd_batch_of_segments(pkg, orc):
             p.coadd_batch(0, n, 5)
 
 
+def test_coadd_batch_after_batched_launches(pkg):
+    """the ring of kept f32 tiles is filled from inside a batched launch (segment s of the launch -> tile
+    (counter + s) % ring): the co-add of the last segments equals the one after per-segment launches, also when
+    the ring wraps inside a launch"""
+    import torch
+    T, n, nseg = 64, 2, 6
+    data = np.empty((nseg, n, 2, T * 12500), np.uint8)
+    for s in range(nseg):
+        for a in range(n):
+            data[s, a, 0], data[s, a, 1] = make_input(pkg, T, seed=81, antenna=a, sample0=s * T * 12500, **RFI)
+    d_in = torch.from_numpy(data).cuda()
+    res = []
+    for mb in (1, 0, 4):
+        with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, n_antennas=n, keep_power=1, power_segments=4,
+                          max_batch_segments=mb) as p:
+            p.coadd_init()
+            d_main = torch.zeros((nseg, n, p.out_bytes), dtype=torch.uint8, device="cuda")
+            d_raw = torch.zeros_like(d_main)
+            p.process_device(n, nseg, d_in.data_ptr(), d_main.data_ptr(), d_raw.data_ptr())
+            p.sync()
+            fb, sm = p.coadd_batch(0, n, 4)
+            res.append((fb.copy(), sm.copy(), p.get_power_f32(1, 0)))
+    for r in res[1:]:
+        assert np.array_equal(res[0][0], r[0]) and np.array_equal(res[0][1], r[1]) and np.array_equal(res[0][2], r[2])
+
+
 def test_vdif_missing_and_invalid_frames_become_dropped_samples(pkg, orc):
     """frames the writer never delivered (absent, or marked invalid) are zeros = dropped data"""
     T = 16
