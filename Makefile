@@ -10,9 +10,10 @@ PKG      := vlite-fast_b200
 CSRC     := $(PKG)/csrc
 HOST     := $(PKG)/host
 LIB      := $(PKG)/libvlitefast.so
+TESTLIB  := $(PKG)/libvlitefast_testing.so
 GENLIB   := $(PKG)/libvlitegen.so
 
-all: $(LIB) $(GENLIB) host oracle build/vf_fft_hosttest scripts/ubench/fp32_rate
+all: $(LIB) $(TESTLIB) $(GENLIB) host oracle build/vf_fft_hosttest scripts/ubench/fp32_rate
 
 build:
 	mkdir -p build
@@ -23,8 +24,21 @@ build/vf_kernels.o: $(CSRC)/vf_kernels.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft125
 build/vf_api.o: $(CSRC)/vf_api.cu $(CSRC)/vf_kernels.h include/vlitefast.h | build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
+# -Bsymbolic: calls between the two objects bind inside the library, so that the product and the testing
+# build can be loaded into one process (tests) without interposing each other's functions
 $(LIB): build/vf_kernels.o build/vf_api.o
-	$(NVCC) -shared $(GENCODE) -o $@ $^ -ldl
+	$(NVCC) -shared $(GENCODE) -Xlinker -Bsymbolic -o $@ $^ -ldl
+
+# the same sources with -DVF_TESTING: adds the monolithic channeliser (vf_config.k1_threads) and
+# vf_debug_division (csrc/vf_testing.h).  Loaded by tests/ for A/B comparisons only.
+build/vf_kernels_t.o: $(CSRC)/vf_kernels.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft12500.cuh $(CSRC)/vf_fft_consts.h | build
+	$(NVCC) $(NVFLAGS) -DVF_TESTING -c $< -o $@
+
+build/vf_api_t.o: $(CSRC)/vf_api.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_testing.h include/vlitefast.h | build
+	$(NVCC) $(NVFLAGS) -DVF_TESTING -c $< -o $@
+
+$(TESTLIB): build/vf_kernels_t.o build/vf_api_t.o
+	$(NVCC) -shared $(GENCODE) -Xlinker -Bsymbolic -o $@ $^ -ldl
 
 # GPU baseband generator: its own library, the only one that links cuFFT
 $(GENLIB): $(CSRC)/vf_genbase_gpu.cu include/vlitegen.h | build
@@ -44,7 +58,7 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf build $(LIB) $(GENLIB)
+	rm -rf build $(LIB) $(TESTLIB) $(GENLIB)
 	$(MAKE) -C oracle clean
 
 .PHONY: all host oracle clean

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VF_ABI_VERSION 1
+#define VF_ABI_VERSION 2
 
 enum {
   VF_OK = 0,
@@ -64,13 +64,17 @@ typedef struct vf_config {
   int inject_frb;      /* 0      -i: allow vf_set_frb_injection                     */
   int gpu_id;          /* 0      -g                                                 */
   int n_antennas;      /* 1      antennas batched on this handle                    */
-  int k1_threads;      /* 0      0 = pipelined channeliser (default); 320, 512 or 640 = monolithic
-                                 channeliser with that many threads (A/B comparison)          */
+  int k1_threads;      /* 0      must be 0 (the pipelined channeliser).  Testing builds of the library
+                                 (libvlitefast_testing.so) also take 320, 512 or 640: the monolithic
+                                 channeliser with that many threads, for A/B comparison       */
   int power_segments;  /* 0      f32 tiles kept for this many consecutive segments (0 = 1): lets
                                  vf_coadd_batch reduce a whole second in one collective       */
   int max_batch_segments;/* 0    vf_process_device: consecutive segments per launch pair (0 = up to 16, 1 = one
                                  launch pair per segment); statistics dumps, histogram and FRB injection imply 1 */
-  int reserved[5];
+  int numa_pin;       /* 0      1 = vf_create binds the calling thread (and so the pinned buffers it allocates
+                                 afterwards) to the CPUs of the GPU's NUMA node, read from sysfs           */
+  double dag_thresh;   /* 3.0    DAG_THRESH: a 500-sample block is excised when its statistic exceeds this  */
+  double min_weight;   /* 0.2    MIN_WEIGHT: FFT time steps below this excision weight leave the scrunches  */
 } vf_config;
 
 typedef struct vf_handle vf_handle;
@@ -91,7 +95,8 @@ size_t vf_segment_out_bytes (const vf_handle *h);
 size_t vf_segment_in_samples (const vf_handle *h);   /* per pol: ffts_per_seg * 12500 */
 
 /* One segment of one antenna, pol-planar HOST input -- exactly the reference's
- * device-edge contract (loop body src/process_baseband.cu:1108-1375).
+ * device-edge contract (loop body src/process_baseband.cu:1108-1375).  antenna
+ * (0 .. n_antennas-1) selects the bandpass state, statistics and kept tile.
  * fb_main receives the excised stream (rfi_mode 1, 2) or the raw stream
  * (rfi_mode 0); fb_raw the raw stream of rfi_mode 2 (may be NULL).
  * Synchronous: returns with the outputs on the host. */
@@ -137,12 +142,18 @@ int vf_sync (vf_handle *h);
 /* elapsed device time between the start and end of the last vf_process_device
  * / vf_process_* call, from CUDA events on the library's stream (ms) */
 int vf_last_elapsed_ms (vf_handle *h, float *total_ms, float *k1_ms, float *k2_ms);
+/* Device-side stopwatch (CUDA events) over everything enqueued on the handle's streams -- segments and co-adds --
+ * between the two calls; vf_timer_end waits for that work and returns the elapsed milliseconds. */
+int vf_timer_begin (vf_handle *h);
+int vf_timer_end (vf_handle *h, float *ms);
 /* profiling aid: serial != 0 stops consecutive segments from overlapping, which makes k1_ms / k2_ms
  * above pure kernel execution times (with overlap they include waiting for SMs) */
 int vf_set_serial (vf_handle *h, int serial);
-/* self-check: the normaliser divides with a packed, branch-free sequence; this runs it beside CUDA's
- * correctly rounded division on n (even) operand pairs p / b so that a test can compare the bits */
-int vf_debug_division (vf_handle *h, const float *p, const float *b, float *q_packed, float *q_ref, size_t n);
+
+/* Bind the calling thread to the CPUs local to the GPU's PCI function (sysfs local_cpulist) before it allocates
+ * pinned buffers; vf_config.numa_pin makes vf_create do this.  cpulist (optional, cap bytes) receives what was
+ * applied, "" if the platform exposes no locality. */
+int vf_bind_thread_to_gpu (int gpu_id, char *cpulist, size_t cap);
 
 /* pinned host memory helpers (cudaMallocHost, :578-579) */
 int vf_host_alloc (void **p, size_t bytes);
@@ -187,9 +198,12 @@ int vf_set_frb_injection (vf_handle *h, int nfft_since_frb, float dm, float widt
 
 /* ---- co-add (replaces scripts/start_coadd + external agdadacoadd, and the
  * per-segment ring write at src/process_baseband.cu:1416-1422) -------------
- * Sum of the main-stream f32 tiles of the handle's n_antennas (last segment),
- * optionally all-reduced over `ranks` processes with NCCL, scaled by
- * 1/sqrt(total antennas) and digitised on rank `root`.  Needs keep_power. */
+ * Sum of the main-stream f32 tiles of the antennas of the last launch (last
+ * segment), reduced over `nranks` processes with NCCL together with the count
+ * of antennas that kept each scrunched row (an antenna whose row was zeroed by
+ * the excision weights, src/pb_kernels.cu:616-623, does not count), divided by
+ * sqrt (count) and digitised on rank `root`.  total_antennas is informative
+ * (the divisor is the reduced count).  Needs keep_power. */
 int vf_coadd_init (vf_handle *h, int nranks, int rank, const void *nccl_unique_id /*128 B*/);
 int vf_coadd_unique_id (void *out128);               /* ncclGetUniqueId */
 int vf_coadd_segment (vf_handle *h, int root, int total_antennas, uint8_t *fb_coadd /*host, root only*/,

@@ -43,6 +43,21 @@ def test_config_defaults_are_the_reference_defaults(pkg):
     # src/process_baseband.h:16-55, src/process_baseband.cu:34,349-351
     assert (cfg.nfft, cfg.nscrunch, cfg.ffts_per_seg, cfg.nkurto) == (12500, 8, 1024, 500)
     assert (cfg.chanmin, cfg.chanmax, cfg.nbit, cfg.npol, cfg.rfi_mode) == (2155, 6250, 2, 1, 2)
+    assert (cfg.dag_thresh, cfg.min_weight) == (3.0, 0.2)      # DAG_THRESH, MIN_WEIGHT, src/process_baseband.h:42,45
+    assert ctypes.sizeof(cfg) == 96
+
+
+def test_testing_hooks_are_not_in_the_product_library(pkg):
+    """the monolithic channeliser and vf_debug_division exist in libvlitefast_testing.so only"""
+    L, LT = pkg.lib(), pkg.lib(testing=True)
+    assert not hasattr(L, "vf_debug_division") and hasattr(LT, "vf_debug_division")
+    for n in declared("include/vlitefast.h"):
+        assert hasattr(LT, n), n
+    cfg = pkg.VfConfig()
+    L.vf_config_default(ctypes.byref(cfg))
+    cfg.k1_threads = 640
+    h = ctypes.c_void_p()
+    assert L.vf_create(ctypes.byref(cfg), ctypes.byref(h)) == 1 and not h
 
 
 def test_strerror_and_bad_config(pkg):

@@ -192,7 +192,7 @@ def test_pipelined_channeliser_stress(pkg, mode):
         ins = [make_input(pkg, T, seed=90 + T, antenna=a, **gen) for a in range(n)]
         outs = []
         for nt in (640, 0):
-            with pkg.Pipeline(ffts_per_seg=T, nbit=8, npol=2, rfi_mode=mode, n_antennas=n, k1_threads=nt) as p:
+            with pkg.Pipeline(testing=True, ffts_per_seg=T, nbit=8, npol=2, rfi_mode=mode, n_antennas=n, k1_threads=nt) as p:
                 runs = []
                 for _ in range(3):
                     m, r = p.process_batch([i[0] for i in ins], [i[1] for i in ins])
@@ -247,7 +247,7 @@ def _k1_variants(pkg, T, n_seg):
     p0, p1 = make_input(pkg, T, seed=60, **RFI)
     outs = []
     for nt in (0, 320, 512, 640) if T == 16 else (0, 640):
-        with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, k1_threads=nt, keep_stats=1, do_histo=1) as p:
+        with pkg.Pipeline(testing=True, ffts_per_seg=T, nbit=8, rfi_mode=2, k1_threads=nt, keep_stats=1, do_histo=1) as p:
             for _ in range(n_seg):          # several launches: the item counter is never reset
                 o = p.process_segment(p0, p1)
             outs.append(o + (p.get_mask(), p.get_stats()))
@@ -410,7 +410,7 @@ def test_packed_division_is_correctly_rounded(pkg):
     b[192:256] = 1e32
     p[256:512] = b[256:512] * np.float32(11.0)
     p[512:768] = np.nextafter(b[512:768], np.float32(np.inf))
-    with pkg.Pipeline(ffts_per_seg=8) as pl:
+    with pkg.Pipeline(testing=True, ffts_per_seg=8) as pl:
         qp, qr = pl.debug_division(p, b)
     ok = (qp.view(np.uint32) == qr.view(np.uint32)) | (np.isnan(qp) & np.isnan(qr))
     ok[64:128] = True             # +inf dividends: the quotient is never used (weight 0)
@@ -419,3 +419,144 @@ def test_packed_division_is_correctly_rounded(pkg):
         want = (p.astype(np.float64) / b.astype(np.float64)).astype(np.float32)
     sel = np.isfinite(want) & (want > 1e-30)
     assert np.array_equal(qr[sel], want[sel])
+
+
+def test_single_antenna_entry_points_on_a_multi_antenna_handle(pkg):
+    """vf_process_segment / vf_process_vdif take the antenna: its own bandpass, statistics and kept tile"""
+    T, n = 16, 3
+    nfr = T * 12500 // 5000
+    g = pkg.GenParams.default(seed=33, **RFI)
+    ins = [(pkg.gen_samples(g, a, 0, 0, T * 12500), pkg.gen_samples(g, a, 1, 0, T * 12500)) for a in range(n)]
+    ins2 = [(pkg.gen_samples(g, a, 0, T * 12500, T * 12500), pkg.gen_samples(g, a, 1, T * 12500, T * 12500)) for a in range(n)]
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, n_antennas=n, keep_power=1, keep_stats=1) as pb:
+        pb.process_batch([i[0] for i in ins], [i[1] for i in ins])
+        want = pb.process_batch([i[0] for i in ins2], [i[1] for i in ins2])       # second segment: carried bandpass
+        wmask = [pb.get_mask(a) for a in range(n)]
+        wave = [pb.get_power_f32(a, 0) for a in range(n)]
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, n_antennas=n, keep_power=1, keep_stats=1) as p:
+        for a in (2, 0, 1):                                   # any order, one antenna at a time
+            p.process_segment(*ins[a], antenna=a)
+        got = {}
+        for a in (1, 2, 0):
+            if a == 1:      # the raw-frame form for one of them
+                frames = pkg.gen_vdif_second(g, a, 0, nfr, nfr)      # frames nfr..2nfr-1 of second 0 = samples T*12500..
+                got[a] = p.process_vdif(frames, nfr, antenna=a)
+            else:
+                got[a] = p.process_segment(*ins2[a], antenna=a)
+        for a in range(n):
+            assert np.array_equal(got[a][0], want[0][a]) and np.array_equal(got[a][1], want[1][a]), a
+            assert np.array_equal(p.get_mask(a), wmask[a]), a
+            assert np.array_equal(p.get_power_f32(a, 0), wave[a]), a
+        with pytest.raises(pkg.VfError) as e:
+            p.process_segment(*ins[0], antenna=n)
+        assert e.value.code == 1
+
+
+def test_statistics_follow_the_slot_of_the_last_segment(pkg, orc):
+    """statistics and histogram buffers are per slot; after segments that alternate between the two
+    slots (vf_process_device, vf_submit_async x2) vf_get_stats returns those of the last segment, unmixed"""
+    import torch
+    T, nseg = 64, 3
+    segs = [make_input(pkg, T, seed=21, sample0=s * T * 12500, **RFI) for s in range(nseg)]
+    o = orc.OracleChain(T, 8, 1, 2)
+    for s in segs:
+        o.process_segment(*s)
+    def check(p):
+        st = p.get_stats()
+        for k in ("pow", "kur", "pow_fb", "kur_fb", "weights", "histo"):
+            assert np.array_equal(st[k], o.get(k), equal_nan=True), k
+        assert np.array_equal(p.get_mask(), o.mask())
+    data = np.stack([np.stack(s) for s in segs])[:, None]          # [seg][1][2][n]
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, keep_stats=1, do_histo=1) as p:
+        d_in = torch.from_numpy(np.ascontiguousarray(data)).cuda()
+        d_main = torch.zeros((nseg, 1, p.out_bytes), dtype=torch.uint8, device="cuda")
+        d_raw = torch.zeros_like(d_main)
+        p.process_device(1, nseg, d_in.data_ptr(), d_main.data_ptr(), d_raw.data_ptr())
+        check(p)
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, keep_stats=1, do_histo=1) as p:
+        outs = [(np.empty(p.out_bytes, np.uint8), np.empty(p.out_bytes, np.uint8)) for _ in range(nseg)]
+        for s in range(nseg):
+            if s >= 2:
+                p.wait(s & 1)
+            p.submit_async(s & 1, [segs[s][0]], [segs[s][1]], [outs[s][0]], [outs[s][1]])
+        p.wait(1); p.wait(0)
+        check(p)
+
+
+def _row_kept(w, min_weight=0.2):
+    """tscrunch_weights' row rule (src/pb_kernels.cu:616-623) from the step weights [T]"""
+    T = w.size
+    kept = np.zeros(T // 8, bool)
+    for t8 in range(T // 8):
+        ws = np.float32(0)
+        for j in range(8):
+            x = w[t8 * 8 + j]
+            if x != 0 and float(x) >= min_weight:
+                ws = np.float32(ws + x)
+        kept[t8] = float(np.float32(ws / np.float32(8))) >= min_weight
+    return kept
+
+
+def test_coadd_counts_the_antennas_that_kept_the_row(pkg, orc):
+    """values and counts are summed, the sum is divided by sqrt (count): an antenna whose scrunched row
+    was zeroed (dropped data) does not dilute the others"""
+    T, n = 32, 3
+    ins = [list(make_input(pkg, T, seed=71, antenna=a, **RFI)) for a in range(n)]
+    ins[1][0] = ins[1][0].copy(); ins[1][1] = ins[1][1].copy()
+    ins[1][0][:16 * 12500] = 0; ins[1][1][:16 * 12500] = 0          # antenna 1: time steps 0..15 dropped -> rows 0, 1 zeroed
+    ins[2][0] = ins[2][0].copy(); ins[2][1] = ins[2][1].copy()
+    ins[2][0][8 * 12500:16 * 12500] = 0; ins[2][1][8 * 12500:16 * 12500] = 0      # antenna 2: row 1
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=1, n_antennas=n, keep_power=1) as p:
+        p.process_batch([i[0] for i in ins], [i[1] for i in ins])
+        p.coadd_init()
+        fb, sm = p.coadd_segment(0, n)
+    tiles, kept = [], []
+    for a in range(n):
+        o = orc.OracleChain(T, 8, 1, 1)
+        o.process_segment(*ins[a])
+        tiles.append(o.ave_trimmed("main"))
+        kept.append(_row_kept(o.get("weights")[:T]))
+    cnt = np.sum(kept, axis=0)
+    assert list(cnt) == [2, 1, 3, 3]
+    osum = tiles[0] + tiles[1] + tiles[2]
+    assert np.all(tiles[1][0, :2] == 0) and np.all(tiles[2][0, 1] == 0)
+    assert np.abs(sm - osum).max() < 5e-4
+    full = np.zeros((1, T // 8, 6251), np.float32)
+    full[:, :, 2155:2155 + 4096] = osum / np.sqrt(cnt.astype(np.float32))[None, :, None]
+    want = np.empty(fb.size, np.uint8)
+    orc.liba().orc_digitise(full.ctypes.data, want.ctypes.data, T // 8, 1, 8)
+    check_bytes(fb, want, 8, "coadd with counts")
+
+
+def test_coadd_sums_only_the_antennas_of_the_last_launch(pkg, orc):
+    """a handle for 3 antennas that last processed 2 co-adds those 2 (no stale tile)"""
+    T, n = 16, 3
+    ins = [make_input(pkg, T, seed=72, antenna=a, **RFI) for a in range(n)]
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=0, n_antennas=n, keep_power=1) as p:
+        p.coadd_init()
+        p.process_batch([i[0] for i in ins], [i[1] for i in ins])
+        p.reset_bandpass()
+        p.process_batch([i[0] for i in ins[:2]], [i[1] for i in ins[:2]])
+        fb, sm = p.coadd_segment(0, 2)
+        t0, t1 = p.get_power_f32(0, 0), p.get_power_f32(1, 0)
+    assert np.array_equal(sm, t0 + t1)
+
+
+def test_thresholds_are_configurable(pkg):
+    """dag_thresh / min_weight (DAG_THRESH, MIN_WEIGHT of src/process_baseband.h:42,45) are carried by vf_config"""
+    T = 32
+    p0, p1 = make_input(pkg, T, seed=14, **RFI)
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=1, keep_stats=1) as p:
+        p.process_segment(p0, p1)
+        dag, m_def = p.get_stats()["dag"][:T * 25].reshape(T, 25), p.get_mask()
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=1, keep_stats=1, dag_thresh=1.5, min_weight=0.9, keep_power=1) as p:
+        p.process_segment(p0, p1)
+        m, w = p.get_mask(), p.get_stats()["weights"][:T]
+        ave = p.get_power_f32(0, 0)
+    want = ((dag > np.float32(1.5)).astype(np.uint32) << np.arange(25, dtype=np.uint32)).sum(axis=1).astype(np.uint32)
+    assert np.array_equal(m, want) and not np.array_equal(m, m_def)
+    kept = _row_kept(w, 0.9)
+    assert 0 < kept.sum() < kept.size                        # the test input must exercise both outcomes
+    assert np.all(ave[0, ~kept] == 0) and np.all(np.abs(ave[0, kept]).max(axis=1) > 0)
+    with pytest.raises(pkg.VfError):
+        pkg.Pipeline(ffts_per_seg=T, dag_thresh=-1.0)

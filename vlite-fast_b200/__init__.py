@@ -11,10 +11,10 @@ is loaded through ``__graft_entry__.load_package()`` under the module name
 ``vlite_fast_b200``.
 """
 from .sharding import antennas_of_rank, coadd_scale
-from .binding import (VfConfig, Pipeline, VfError, lib, hostlib, GenParams, gen_samples,
+from .binding import (VfConfig, Pipeline, bind_thread_to_gpu, VfError, lib, hostlib, GenParams, gen_samples,
                       gen_vdif_second, NFFT, NCHANOUT, NSCRUNCH, NSUB, VD_FRM, VD_DAT,
                       FRAMES_PER_SEC, VfgConfig, GpuGenerator, genlib)
 
-__all__ = ["VfConfig", "Pipeline", "VfError", "lib", "hostlib", "GenParams", "gen_samples",
+__all__ = ["VfConfig", "Pipeline", "bind_thread_to_gpu", "VfError", "lib", "hostlib", "GenParams", "gen_samples",
            "gen_vdif_second", "NFFT", "NCHANOUT", "NSCRUNCH", "NSUB", "VD_FRM", "VD_DAT",
            "FRAMES_PER_SEC", "VfgConfig", "GpuGenerator", "genlib"]

@@ -28,7 +28,8 @@ class VfConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "abi_version", "nfft", "nscrunch", "ffts_per_seg", "nkurto", "chanmin", "chanmax", "nbit",
         "npol", "rfi_mode", "do_histo", "keep_stats", "keep_power", "inject_frb", "gpu_id",
-        "n_antennas", "k1_threads", "power_segments", "max_batch_segments")] + [("reserved", C.c_int * 5)]
+        "n_antennas", "k1_threads", "power_segments", "max_batch_segments", "numa_pin")] + [
+        ("dag_thresh", C.c_double), ("min_weight", C.c_double)]
 
 
 def _load(name):
@@ -36,19 +37,20 @@ def _load(name):
     if not os.path.exists(path):
         raise ImportError("%s is not built: run `make` (or __graft_entry__.build()) first; "
                           "there is no Python or CPU fallback" % path)
-    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+    return C.CDLL(path, mode=C.RTLD_LOCAL)
 
 
-_lib = None
+_lib = {}
 _hostlib = None
 
 
-def lib():
-    """libvlitefast.so with argument types declared."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    L = _load("libvlitefast.so")
+def lib(testing=False):
+    """libvlitefast.so with argument types declared.  testing=True: libvlitefast_testing.so, the same sources
+    built with -DVF_TESTING (monolithic channeliser variants + vf_debug_division, csrc/vf_testing.h) -- for the
+    A/B tests only."""
+    if testing in _lib:
+        return _lib[testing]
+    L = _load("libvlitefast_testing.so" if testing else "libvlitefast.so")
     vp, u8p, i, sz = C.c_void_p, C.c_void_p, C.c_int, C.c_size_t
     pp = C.POINTER(C.c_void_p)
     L.vf_config_default.argtypes = [C.POINTER(VfConfig)]
@@ -67,9 +69,13 @@ def lib():
     L.vf_process_device.argtypes = [vp, i, i, vp, vp, vp]
     L.vf_sync.argtypes = [vp]
     L.vf_set_serial.argtypes = [vp, i]
-    L.vf_debug_division.argtypes = [vp, vp, vp, vp, vp, sz]
+    L.vf_timer_begin.argtypes = [vp]
+    L.vf_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
+    if testing:
+        L.vf_debug_division.argtypes = [vp, vp, vp, vp, vp, sz]
     fp = C.POINTER(C.c_float)
     L.vf_last_elapsed_ms.argtypes = [vp, fp, fp, fp]
+    L.vf_bind_thread_to_gpu.argtypes = [i, C.c_char_p, sz]
     L.vf_host_alloc.argtypes = [C.POINTER(vp), sz]
     L.vf_host_free.argtypes = [vp]
     L.vf_get_stats.argtypes = [vp, i] + [vp] * 8
@@ -84,7 +90,7 @@ def lib():
     L.vf_coadd_unique_id.argtypes = [vp]
     L.vf_coadd_segment.argtypes = [vp, i, i, vp, vp]
     L.vf_coadd_batch.argtypes = [vp, i, i, i, vp, vp, i]
-    _lib = L
+    _lib[testing] = L
     return L
 
 
@@ -146,11 +152,20 @@ def _ptr(a):
     return a.ctypes.data
 
 
+def bind_thread_to_gpu(gpu_id):
+    """vf_bind_thread_to_gpu: returns the CPU list applied ('' when the platform exposes none)"""
+    buf = C.create_string_buffer(1024)
+    rc = lib().vf_bind_thread_to_gpu(gpu_id, buf, 1024)
+    if rc:
+        raise VfError(rc, "vf_bind_thread_to_gpu")
+    return buf.value.decode()
+
+
 class Pipeline:
     """One vf_handle.  Keyword arguments are vf_config fields."""
 
-    def __init__(self, **kw):
-        L = lib()
+    def __init__(self, testing=False, **kw):
+        L = lib(testing)
         cfg = VfConfig()
         L.vf_config_default(C.byref(cfg))
         for k, v in kw.items():
@@ -195,12 +210,12 @@ class Pipeline:
             raise VfError(rc, self.L.vf_last_error(self.h).decode())
 
     # ---- processing -------------------------------------------------------
-    def process_segment(self, pol0, pol1):
+    def process_segment(self, pol0, pol1, antenna=0):
         """vf_process_segment: returns (fb_main, fb_raw or None)."""
         main = np.empty(self.out_bytes, np.uint8)
         raw = np.empty(self.out_bytes, np.uint8) if self.cfg.rfi_mode == 2 else None
         nb = C.c_size_t()
-        self._ck(self.L.vf_process_segment(self.h, 0, _ptr(pol0), _ptr(pol1), pol0.size,
+        self._ck(self.L.vf_process_segment(self.h, antenna, _ptr(pol0), _ptr(pol1), pol0.size,
                                            _ptr(main), _ptr(raw), C.byref(nb)))
         assert nb.value == self.out_bytes
         return main, raw
@@ -227,11 +242,11 @@ class Pipeline:
     def wait(self, slot):
         self._ck(self.L.vf_wait(self.h, slot))
 
-    def process_vdif(self, frames, first_frame):
+    def process_vdif(self, frames, first_frame, antenna=0):
         main = np.empty(self.out_bytes, np.uint8)
         raw = np.empty(self.out_bytes, np.uint8) if self.cfg.rfi_mode == 2 else None
         nb = C.c_size_t()
-        self._ck(self.L.vf_process_vdif(self.h, 0, _ptr(frames), frames.size // VD_FRM, first_frame,
+        self._ck(self.L.vf_process_vdif(self.h, antenna, _ptr(frames), frames.size // VD_FRM, first_frame,
                                         _ptr(main), _ptr(raw), C.byref(nb)))
         return main, raw
 
@@ -250,6 +265,14 @@ class Pipeline:
 
     def sync(self):
         self._ck(self.L.vf_sync(self.h))
+
+    def timer_begin(self):
+        self._ck(self.L.vf_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_float()
+        self._ck(self.L.vf_timer_end(self.h, C.byref(ms)))
+        return ms.value
 
     def last_elapsed_ms(self):
         a, b, c = C.c_float(), C.c_float(), C.c_float()
@@ -321,6 +344,10 @@ class Pipeline:
         sm = np.empty((n_seg, self.cfg.npol, self.ntime, NCHANOUT), np.float32) if want else None
         self._ck(self.L.vf_coadd_batch(self.h, root, total_antennas, n_seg, _ptr(fb), _ptr(sm), 1 if (wait or want) else 0))
         return fb, sm
+
+    def coadd_batch_into(self, root, total_antennas, n_seg, fb_host=None, sum_host=None, wait=False):
+        """vf_coadd_batch into caller-owned (pinned) host arrays; None = not wanted (every rank but the root)"""
+        self._ck(self.L.vf_coadd_batch(self.h, root, total_antennas, n_seg, _ptr(fb_host), _ptr(sum_host), 1 if wait else 0))
 
     def coadd_segment(self, root, total_antennas, want=True):
         n = self.cfg.npol * self.ntime * NCHANOUT

@@ -19,10 +19,15 @@
 #include <stdlib.h>
 #include <string.h>
 #include <dlfcn.h>
+#include <sched.h>
+#include <ctype.h>
 #include <vector>
 #include <cuda_runtime.h>
 #include "vlitefast.h"
 #include "vf_kernels.h"
+#ifdef VF_TESTING
+#include "vf_testing.h"
+#endif
 
 #define VF_MAX_TIMED_SEG 256
 
@@ -41,6 +46,10 @@ struct vf_slot {
   uint32_t first_frame;
   unsigned int *d_work;       /* item counter of the pipelined channeliser; never reset: */
   unsigned int work_base;     /* its value when the next launch starts                   */
+  /* statistics dumps of the segment this slot processed last (keep_stats / do_histo): one set per slot,
+   * because the channelisers of the two slots run on independent streams */
+  float *pw, *kur, *dag, *pw_fb, *kur_fb, *dag_fb;
+  unsigned int *histo;
 };
 
 /* minimal NCCL surface, resolved with dlopen at vf_coadd_init */
@@ -67,31 +76,33 @@ struct vf_handle {
   cudaStream_t coadd_st;      /* co-add runs beside the next segments, not in front of them */
   vf_slot slot[2];
   int batch_cap;              /* consecutive segments the tile / weight / mask buffers of a slot hold */
-  int last_batch, last_n_ant; /* segments / antennas of the last launch (the getters look at its last segment) */
+  int last_n_ant;             /* antennas of the last launch (the co-add sums that many tiles) */
+  long *ant_seg;              /* per handle antenna: segments enqueued so far (position in the ring of kept tiles) */
+  struct vf_ant_last { int slot; size_t idx; } *ant_last;   /* per handle antenna: slot and index (in that slot's weight /
+                                 mask / tile buffers) of the last segment processed for it */
   int next_slot;              /* slot of the next synchronous segment */
-  int last_slot;              /* slot that holds the last processed segment */
   cudaEvent_t ev_k2_last;     /* completion of the most recent K2 */
   int have_k2_last;
   float2 *bp_raw, *bp_kur;    /* [n_ant][4096] (pol0, pol1) */
   float2 *tw;                 /* tw1 | tw5 | tw500 */
   float *wtab;                /* [26] */
-  float *pw, *kur, *dag, *pw_fb, *kur_fb, *dag_fb;
-  unsigned int *histo;
   float *ave_main, *ave_raw;  /* [ave_nseg][n_ant][npol][T/8][4096] */
+  float *rowok;               /* [ave_nseg][n_ant][T/8]: 1 = scrunched row of the main stream kept, 0 = zeroed (co-add count) */
   int ave_nseg;               /* tiles kept (ring over consecutive segments) */
-  long seg_counter;           /* segments enqueued so far */
   float *frb_delays;
   int frb_nfft_since; float frb_width, frb_amp; float frb_dm;
   double dagc[5], dagc_fb[5];
   /* timing */
   cudaEvent_t ev_t0, ev_t1;
+  cudaEvent_t ev_u0, ev_u1;   /* vf_timer_begin / vf_timer_end */
   cudaEvent_t ev_ka[VF_MAX_TIMED_SEG], ev_kb[VF_MAX_TIMED_SEG], ev_kc[VF_MAX_TIMED_SEG];
   int n_timed, timed_valid;
   /* co-add */
   vf_nccl_comm comm; int nranks, rank;
   struct { cudaEvent_t ev; long lo, hi; int pending; } coadd_batch[2];   /* the last two co-add batches */
   int coadd_next;
-  float *coadd_sum; uint8_t *coadd_out;
+  float *coadd_sum;           /* [ave_nseg] summed tiles, then [ave_nseg][T/8] contributing-antenna counts: one reduce */
+  uint8_t *coadd_out;
   int debug_sync, serial;
   char err[512];
 };
@@ -145,6 +156,8 @@ int vf_config_default (vf_config *c)
   c->npol = 1;                   /* :349 */
   c->rfi_mode = 2;               /* :351 */
   c->n_antennas = 1;
+  c->dag_thresh = 3.0;           /* DAG_THRESH, src/process_baseband.h:42 */
+  c->min_weight = 0.2;           /* MIN_WEIGHT, :45 */
   return VF_OK;
 }
 
@@ -199,12 +212,6 @@ static int vf_alloc_slot (vf_handle *h, vf_slot *s)
 
 /* segments that one launch pair may cover (vf_process_device): the statistics dumps, the histogram
  * and the FRB injection are per segment, so they keep launches per segment */
-/* index of (last segment of the last launch, antenna) in the slot's weight / mask / tile buffers */
-static size_t vf_last_index (const vf_handle *h, int antenna)
-{
-  return (size_t) (h->last_batch - 1) * h->last_n_ant + antenna;
-}
-
 static int vf_max_batch (const vf_handle *h)
 {
   const vf_config &c = h->cfg;
@@ -241,15 +248,18 @@ int vf_destroy (vf_handle *h)
     cudaFree (s->w); cudaFree (s->mask); cudaFree (s->d_out_main); cudaFree (s->d_out_raw);
     cudaFree (s->d_bad); if (s->h_bad) cudaFreeHost (s->h_bad);
     cudaFree (s->d_work);
+    cudaFree (s->pw); cudaFree (s->pw_fb); cudaFree (s->histo);
     if (s->ev_k2) cudaEventDestroy (s->ev_k2);
     if (s->ev_done) cudaEventDestroy (s->ev_done);
     if (s->st) cudaStreamDestroy (s->st);
   }
   cudaFree (h->bp_raw); cudaFree (h->bp_kur); cudaFree (h->tw); cudaFree (h->wtab);
-  cudaFree (h->pw); cudaFree (h->pw_fb); cudaFree (h->histo); cudaFree (h->ave_main); cudaFree (h->ave_raw);
+  cudaFree (h->ave_main); cudaFree (h->ave_raw); cudaFree (h->rowok); free (h->ant_last); free (h->ant_seg);
   cudaFree (h->frb_delays); cudaFree (h->coadd_sum); cudaFree (h->coadd_out);
   if (h->ev_t0) cudaEventDestroy (h->ev_t0);
   if (h->ev_t1) cudaEventDestroy (h->ev_t1);
+  if (h->ev_u0) cudaEventDestroy (h->ev_u0);
+  if (h->ev_u1) cudaEventDestroy (h->ev_u1);
   if (h->ev_k2_last) cudaEventDestroy (h->ev_k2_last);
   for (int b = 0; b < 2; ++b) if (h->coadd_batch[b].ev) cudaEventDestroy (h->coadd_batch[b].ev);
   for (int i = 0; i < VF_MAX_TIMED_SEG; ++i) {
@@ -278,7 +288,12 @@ int vf_create (const vf_config *cfg, vf_handle **out)
   if (cfg->rfi_mode < 0 || cfg->rfi_mode > 2) return VF_ERR_ARG;
   if (cfg->n_antennas < 1 || cfg->n_antennas > 4096) return VF_ERR_ARG;
   if (cfg->max_batch_segments < 0 || cfg->max_batch_segments > 64) return VF_ERR_ARG;
+#ifdef VF_TESTING
   if (!(cfg->k1_threads == 0 || cfg->k1_threads == 320 || cfg->k1_threads == 512 || cfg->k1_threads == 640)) return VF_ERR_ARG;
+#else
+  if (cfg->k1_threads != 0) return VF_ERR_ARG;      /* the monolithic channeliser exists in testing builds only */
+#endif
+  if (!(cfg->dag_thresh > 0.) || !(cfg->min_weight >= 0.) || cfg->min_weight > 1.) return VF_ERR_ARG;
 
   int ndev = 0;
   if (cudaGetDeviceCount (&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError (); return VF_ERR_NODEV; }
@@ -289,7 +304,7 @@ int vf_create (const vf_config *cfg, vf_handle **out)
   h->cfg = *cfg;
   *out = h;    /* handed back even on failure so that vf_last_error works; caller destroys */
   h->T = cfg->ffts_per_seg;
-  h->batch_cap = 1; h->last_batch = 1; h->last_n_ant = 1;
+  h->batch_cap = 1; h->last_n_ant = 1;
   h->ntime = h->T / VF_NSCRUNCH;
   h->n_ant = cfg->n_antennas;
   h->nsamp = (size_t) h->T * VF_NFFT;
@@ -302,6 +317,7 @@ int vf_create (const vf_config *cfg, vf_handle **out)
   { const char *e = getenv ("VF_SERIAL"); h->serial = e && *e == '1'; }
 
   CK (cudaSetDevice (cfg->gpu_id));
+  if (cfg->numa_pin) vf_bind_thread_to_gpu (cfg->gpu_id, NULL, 0);
   cudaDeviceProp prop;
   CK (cudaGetDeviceProperties (&prop, cfg->gpu_id));
   if (prop.major < 10)
@@ -354,16 +370,23 @@ int vf_create (const vf_config *cfg, vf_handle **out)
   vf_dag_constants (VF_NKURTO, h->dagc);
   vf_dag_constants (VF_NFFT, h->dagc_fb);
 
-  if (cfg->keep_stats && cfg->rfi_mode) {
-    const size_t nblk = (size_t) h->T * VF_NSUB;
-    CK (cudaMalloc ((void **) &h->pw, na * 6 * nblk * sizeof (float)));
-    h->kur = h->pw + na * 2 * nblk;
-    h->dag = h->pw + na * 4 * nblk;
-    CK (cudaMalloc ((void **) &h->pw_fb, na * 6 * h->T * sizeof (float)));
-    h->kur_fb = h->pw_fb + na * 2 * h->T;
-    h->dag_fb = h->pw_fb + na * 4 * h->T;
+  for (int i = 0; i < 2; ++i) {
+    vf_slot *s = &h->slot[i];
+    if (cfg->keep_stats && cfg->rfi_mode) {
+      const size_t nblk = (size_t) h->T * VF_NSUB;
+      CK (cudaMalloc ((void **) &s->pw, na * 6 * nblk * sizeof (float)));
+      s->kur = s->pw + na * 2 * nblk;
+      s->dag = s->pw + na * 4 * nblk;
+      CK (cudaMalloc ((void **) &s->pw_fb, na * 6 * h->T * sizeof (float)));
+      s->kur_fb = s->pw_fb + na * 2 * h->T;
+      s->dag_fb = s->pw_fb + na * 4 * h->T;
+    }
+    if (cfg->do_histo) CK (cudaMalloc ((void **) &s->histo, na * 512 * sizeof (unsigned int)));
   }
-  if (cfg->do_histo) CK (cudaMalloc ((void **) &h->histo, na * 512 * sizeof (unsigned int)));
+  h->ant_last = (vf_handle::vf_ant_last *) calloc (na, sizeof (*h->ant_last));
+  h->ant_seg = (long *) calloc (na, sizeof (long));
+  if (!h->ant_last || !h->ant_seg) return vf_fail (h, VF_ERR_NOMEM, "out of host memory");
+  for (int a = 0; a < h->n_ant; ++a) h->ant_last[a].idx = (size_t) a;
   h->ave_nseg = cfg->power_segments > 0 ? cfg->power_segments : 1;
   if (cfg->keep_power) {
     const size_t n = (size_t) h->ave_nseg * na * cfg->npol * h->ntime * VF_NCHANOUT;
@@ -373,11 +396,56 @@ int vf_create (const vf_config *cfg, vf_handle **out)
       CK (cudaMalloc ((void **) &h->ave_raw, n * sizeof (float)));
       CK (cudaMemset (h->ave_raw, 0, n * sizeof (float)));
     }
+    const size_t nr = (size_t) h->ave_nseg * na * h->ntime;
+    CK (cudaMalloc ((void **) &h->rowok, nr * sizeof (float)));
+    CK (cudaMemset (h->rowok, 0, nr * sizeof (float)));
   }
   CK (cudaEventCreate (&h->ev_t0));
   CK (cudaEventCreate (&h->ev_t1));
+  CK (cudaEventCreate (&h->ev_u0));
+  CK (cudaEventCreate (&h->ev_u1));
   CK (cudaEventCreateWithFlags (&h->ev_k2_last, cudaEventDisableTiming));
   CK (cudaDeviceSynchronize ());
+  return VF_OK;
+}
+
+/* Bind the calling thread to the CPUs that are local to the GPU (sysfs local_cpulist of its PCI function), so that
+ * pinned buffers the thread allocates afterwards (first touch) and its copies' staging sit on the GPU's NUMA node.
+ * cpulist (optional) receives the list that was applied, "" when the platform exposes none. */
+int vf_bind_thread_to_gpu (int gpu_id, char *cpulist, size_t cap)
+{
+  if (cpulist && cap) cpulist[0] = 0;
+  char bus[32];
+  if (cudaDeviceGetPCIBusId (bus, sizeof (bus), gpu_id) != cudaSuccess) { cudaGetLastError (); return VF_ERR_NODEV; }
+  for (char *c = bus; *c; ++c) *c = (char) tolower (*c);
+  char path[128], line[1024];
+  snprintf (path, sizeof (path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+  FILE *f = fopen (path, "r");
+  if (!f) return VF_OK;                       /* no NUMA information: nothing to do */
+  if (!fgets (line, sizeof (line), f)) line[0] = 0;
+  fclose (f);
+  cpu_set_t set;
+  CPU_ZERO (&set);
+  int n = 0;
+  for (char *p = line; *p && *p != '\n';) {
+    char *e;
+    long a = strtol (p, &e, 10), b = a;
+    if (e == p) break;
+    if (*e == '-') { p = e + 1; b = strtol (p, &e, 10); }
+    for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET ((int) c, &set); ++n; }
+    p = (*e == ',') ? e + 1 : e;
+  }
+  if (n == 0) return VF_OK;
+  /* keep only CPUs this process may use (cgroup / taskset) */
+  cpu_set_t cur;
+  if (sched_getaffinity (0, sizeof (cur), &cur) == 0) {
+    cpu_set_t both;
+    CPU_AND (&both, &set, &cur);
+    if (CPU_COUNT (&both) == 0) return VF_OK;
+    set = both;
+  }
+  if (sched_setaffinity (0, sizeof (set), &set) != 0) return VF_OK;
+  if (cpulist && cap) { size_t l = strcspn (line, "\n"); if (l >= cap) l = cap - 1; memcpy (cpulist, line, l); cpulist[l] = 0; }
   return VF_OK;
 }
 
@@ -409,13 +477,15 @@ int vf_host_unregister (void *p)
 }
 
 /* ---- the launch sequence of one segment on one slot ---------------------- *
- * d_in: [n_ant][2][T*12500] on the device.  Outputs to d_main / d_raw
- * ([n_ant][out_bytes]).  timed >= 0: record the K1/K2 events of that index. */
-static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_t *d_in,
+ * d_in: [n_ant][2][T*12500] on the device, antenna a of the launch being antenna ant0 + a of the handle
+ * (bandpass state, statistics, kept tiles).  Outputs to d_main / d_raw ([n_ant][out_bytes]).
+ * timed >= 0: record the K1/K2 events of that index. */
+static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int ant0, int n_ant, const uint8_t *d_in,
                                uint8_t *d_main, uint8_t *d_raw, int timed, int n_seg = 1)
 {
   if (n_seg > h->batch_cap) return vf_fail (h, VF_ERR_STATE, "batch of %d segments, buffers hold %d", n_seg, h->batch_cap);
   const vf_config &c = h->cfg;
+  const size_t nblk = (size_t) h->T * VF_NSUB;
   vf_k1_params k1;
   memset (&k1, 0, sizeof (k1));
   k1.in = d_in;
@@ -424,22 +494,26 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
   k1.T = h->T; k1.n_ant = n_ant * n_seg; k1.rfi_mode = c.rfi_mode;   /* (segment, antenna) pairs are the channeliser's antennas */
   k1.P_raw = s->P_raw; k1.P_kur = s->P_kur;
   k1.w = s->w; k1.mask = s->mask;
-  k1.pw = h->pw; k1.kur = h->kur; k1.dag = h->dag;
-  k1.pw_fb = h->pw_fb; k1.kur_fb = h->kur_fb; k1.dag_fb = h->dag_fb;
-  k1.histo = h->histo;
+  if (s->pw) {
+    k1.pw = s->pw + (size_t) ant0 * 2 * nblk; k1.kur = s->kur + (size_t) ant0 * 2 * nblk; k1.dag = s->dag + (size_t) ant0 * 2 * nblk;
+    k1.pw_fb = s->pw_fb + (size_t) ant0 * 2 * h->T; k1.kur_fb = s->kur_fb + (size_t) ant0 * 2 * h->T;
+    k1.dag_fb = s->dag_fb + (size_t) ant0 * 2 * h->T;
+  }
+  if (s->histo) k1.histo = s->histo + (size_t) ant0 * 512;
   k1.tb.tw1 = h->tw; k1.tb.tw5 = h->tw + 500; k1.tb.tw500 = h->tw + 1000;
   memcpy (k1.dagc, h->dagc, sizeof (k1.dagc));
   memcpy (k1.dagc_fb, h->dagc_fb, sizeof (k1.dagc_fb));
+  k1.dag_thresh = c.dag_thresh;
   k1.wtab = h->wtab;
   if (c.inject_frb && h->frb_nfft_since >= 0 && h->frb_delays) {
     k1.frb_delays = h->frb_delays;
     k1.nfft_since_frb = h->frb_nfft_since;
     k1.frb_width = h->frb_width; k1.frb_amp = h->frb_amp;
   }
-  if (h->histo) CK (cudaMemsetAsync (h->histo, 0, (size_t) n_ant * 512 * sizeof (unsigned int), s->st));
+  if (k1.histo) CK (cudaMemsetAsync (k1.histo, 0, (size_t) n_ant * 512 * sizeof (unsigned int), s->st));
   const int n_items = n_ant * n_seg * h->T;
   const int grid = n_items < h->nsm ? n_items : h->nsm;
-  const int threads = c.k1_threads;            /* 0: pipelined kernel; 320/512/640: monolithic kernel (A/B) */
+  const int threads = c.k1_threads;            /* 0: pipelined kernel; 320/512/640: monolithic kernel (testing builds, A/B) */
   if (threads == 0) {
     k1.work_counter = s->d_work;
     k1.work_base = s->work_base;
@@ -453,9 +527,11 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
 
   /* the bandpass makes K2 launches sequential in segment order */
   if (h->have_k2_last) CK (cudaStreamWaitEvent (s->st, h->ev_k2_last, 0));
-  /* this segment overwrites the tile of segment (seg_counter - ave_nseg): wait for a co-add that still reads it */
+  /* segments enqueued so far for these antennas (they advance together): index into the ring of kept tiles */
+  const long seg0 = h->ant_seg[ant0];
+  /* this launch overwrites the tiles of segments [seg0 - ave_nseg, seg0 - ave_nseg + n_seg): wait for a co-add that still reads them */
   for (int b = 0; b < 2; ++b) {
-    const long victim_lo = h->seg_counter - h->ave_nseg, victim_hi = victim_lo + n_seg;    /* [lo, hi) */
+    const long victim_lo = seg0 - h->ave_nseg, victim_hi = victim_lo + n_seg;    /* [lo, hi) */
     if (h->coadd_batch[b].pending && victim_lo < h->coadd_batch[b].hi && victim_hi > h->coadd_batch[b].lo) {
       CK (cudaStreamWaitEvent (s->st, h->coadd_batch[b].ev, 0));
       h->coadd_batch[b].pending = 0;
@@ -464,19 +540,28 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int n_ant, const uint8_
   vf_k2_params k2;
   memset (&k2, 0, sizeof (k2));
   k2.P_raw = s->P_raw; k2.P_kur = s->P_kur; k2.w = s->w; k2.mask = s->mask;
-  k2.bp_raw = h->bp_raw; k2.bp_kur = (c.rfi_mode == 2) ? h->bp_kur : h->bp_raw;
+  k2.bp_raw = h->bp_raw + (size_t) ant0 * VF_NCHANOUT;
+  k2.bp_kur = ((c.rfi_mode == 2) ? h->bp_kur : h->bp_raw) + (size_t) ant0 * VF_NCHANOUT;
   k2.T = h->T; k2.n_ant = n_ant; k2.n_seg = n_seg; k2.rfi_mode = c.rfi_mode; k2.npol = c.npol; k2.nbit = c.nbit;
   /* bp_scale = float(tsamp/tsmooth), src/process_baseband.cu:737-741 */
   k2.bp_scale = (float) (((double) VF_NFFT / 128000000 * VF_NSCRUNCH) / 1.0);
+  k2.min_weight = c.min_weight;
   k2.out_main = d_main; k2.out_raw = d_raw; k2.out_stride = h->out_bytes;
-  { static const char *dbg = getenv ("VF_K2_DEBUG"); k2.debug = dbg ? atoi (dbg) : 0; }
   {
     /* tile slots of these segments in the ring of kept tiles (sized for the handle's n_antennas) */
-    k2.ave_main = h->ave_main; k2.ave_raw = h->ave_raw;
-    k2.ave_seg0 = h->seg_counter; k2.ave_nseg = h->ave_nseg;
-    k2.ave_seg_elems = (size_t) h->n_ant * c.npol * h->ntime * VF_NCHANOUT;
-    h->seg_counter += n_seg;
-    h->last_batch = n_seg; h->last_n_ant = n_ant;
+    const size_t tile1 = (size_t) c.npol * h->ntime * VF_NCHANOUT;
+    k2.ave_main = h->ave_main ? h->ave_main + (size_t) ant0 * tile1 : NULL;
+    k2.ave_raw = h->ave_raw ? h->ave_raw + (size_t) ant0 * tile1 : NULL;
+    k2.ave_seg0 = seg0; k2.ave_nseg = h->ave_nseg;
+    k2.ave_seg_elems = (size_t) h->n_ant * tile1;
+    k2.rowok = h->rowok ? h->rowok + (size_t) ant0 * h->ntime : NULL;
+    k2.rowok_seg_elems = (size_t) h->n_ant * h->ntime;
+    for (int a = 0; a < n_ant; ++a) {
+      h->ant_seg[ant0 + a] = seg0 + n_seg;
+      h->ant_last[ant0 + a].slot = (int) (s - h->slot);
+      h->ant_last[ant0 + a].idx = (size_t) (n_seg - 1) * n_ant + a;
+    }
+    h->last_n_ant = n_ant;
   }
   CK (vf_launch_k2 (k2, s->st));
   if (h->debug_sync) CK (cudaStreamSynchronize (s->st));
@@ -540,7 +625,7 @@ int vf_submit_async (vf_handle *h, int slot, int n_ant,
     CK (cudaMemcpyAsync (s->d_in + (size_t) a * 2 * h->nsamp, pol0[a], h->nsamp, cudaMemcpyHostToDevice, s->st));
     CK (cudaMemcpyAsync (s->d_in + ((size_t) a * 2 + 1) * h->nsamp, pol1[a], h->nsamp, cudaMemcpyHostToDevice, s->st));
   }
-  rc = vf_enqueue_segment (h, s, n_ant, s->d_in, s->d_out_main, s->d_out_raw, -1);
+  rc = vf_enqueue_segment (h, s, 0, n_ant, s->d_in, s->d_out_main, s->d_out_raw, -1);
   if (rc) return rc;
   for (int a = 0; a < n_ant; ++a) {                       /* D2H, :1370-1375 */
     CK (cudaMemcpyAsync (fb_main[a], s->d_out_main + (size_t) a * h->out_bytes, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
@@ -549,7 +634,6 @@ int vf_submit_async (vf_handle *h, int slot, int n_ant,
   }
   CK (cudaEventRecord (s->ev_done, s->st));
   s->pending = 1;
-  h->last_slot = slot;
   return VF_OK;
 }
 
@@ -583,16 +667,43 @@ int vf_process_batch (vf_handle *h, int n_ant,
   return vf_wait (h, slot);
 }
 
+/* one antenna of a multi-antenna handle: the same launch sequence with that antenna's bandpass,
+ * statistics and kept tiles */
+static int vf_submit_one_async (vf_handle *h, int slot, int antenna, const uint8_t *pol0, const uint8_t *pol1,
+                                uint8_t *fb_main, uint8_t *fb_raw)
+{
+  vf_slot *s = &h->slot[slot];
+  CK (cudaSetDevice (h->cfg.gpu_id));
+  CK (cudaMemcpyAsync (s->d_in, pol0, h->nsamp, cudaMemcpyHostToDevice, s->st));      /* H2D, src/process_baseband.cu:1117-1122 */
+  CK (cudaMemcpyAsync (s->d_in + h->nsamp, pol1, h->nsamp, cudaMemcpyHostToDevice, s->st));
+  int rc = vf_enqueue_segment (h, s, antenna, 1, s->d_in, s->d_out_main, s->d_out_raw, -1);
+  if (rc) return rc;
+  CK (cudaMemcpyAsync (fb_main, s->d_out_main, h->out_bytes, cudaMemcpyDeviceToHost, s->st));   /* D2H, :1370-1375 */
+  if (h->cfg.rfi_mode == 2 && fb_raw)
+    CK (cudaMemcpyAsync (fb_raw, s->d_out_raw, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
+  CK (cudaEventRecord (s->ev_done, s->st));
+  s->pending = 1;
+  return VF_OK;
+}
+
 int vf_process_segment (vf_handle *h, int antenna,
                         const uint8_t *pol0, const uint8_t *pol1, size_t nsamp_per_pol,
                         uint8_t *fb_main, uint8_t *fb_raw, size_t *nbytes)
 {
-  if (!h) return VF_ERR_ARG;
-  if (antenna != 0)
-    return vf_fail (h, VF_ERR_ARG, "vf_process_segment drives antenna 0 of the handle; batch the others with vf_process_batch");
-  const uint8_t *p0[1] = { pol0 }, *p1[1] = { pol1 };
-  uint8_t *m[1] = { fb_main }, *r[1] = { fb_raw };
-  int rc = vf_process_batch (h, 1, p0, p1, nsamp_per_pol, m, r);
+  int rc = vf_check_batch (h, 1, nsamp_per_pol);
+  if (rc) return rc;
+  if (antenna < 0 || antenna >= h->n_ant) return vf_fail (h, VF_ERR_ARG, "antenna %d outside 0..%d", antenna, h->n_ant - 1);
+  if (!pol0 || !pol1 || !fb_main) return vf_fail (h, VF_ERR_ARG, "null buffer");
+  const int slot = h->next_slot;
+  if (h->slot[slot].pending) return vf_fail (h, VF_ERR_STATE, "slot %d has an asynchronous segment in flight", slot);
+  rc = vf_timing_begin (h, 0);
+  if (rc) return rc;
+  rc = vf_submit_one_async (h, slot, antenna, pol0, pol1, fb_main, fb_raw);
+  if (rc) return rc;
+  rc = vf_timing_end (h);
+  if (rc) { h->slot[slot].pending = 0; return rc; }
+  h->next_slot ^= 1;
+  rc = vf_wait (h, slot);
   if (rc == VF_OK && nbytes) *nbytes = h->out_bytes;
   return rc;
 }
@@ -602,7 +713,7 @@ int vf_submit_vdif_async (vf_handle *h, int slot, int antenna, const void *frame
 {
   if (!h || !frames || !fb_main) return VF_ERR_ARG;
   if (slot < 0 || slot > 1) return vf_fail (h, VF_ERR_ARG, "bad slot");
-  if (antenna != 0) return vf_fail (h, VF_ERR_ARG, "the VDIF entry points drive antenna 0 of the handle");
+  if (antenna < 0 || antenna >= h->n_ant) return vf_fail (h, VF_ERR_ARG, "antenna %d outside 0..%d", antenna, h->n_ant - 1);
   const size_t per_pol = h->nsamp / VF_VD_DAT;            /* frames per pol per segment */
   if (nframes > 4 * per_pol) return vf_fail (h, VF_ERR_ARG, "%zu frames for a segment of %zu", nframes, 2 * per_pol);
   vf_slot *s = &h->slot[slot];
@@ -629,7 +740,7 @@ int vf_submit_vdif_async (vf_handle *h, int slot, int antenna, const void *frame
   dp.frame0 = first_frame; dp.nframes_per_pol = (long long) per_pol; dp.bad = s->d_bad;
   CK (vf_launch_depack (dp, s->st));
   CK (cudaMemcpyAsync (s->h_bad, s->d_bad, sizeof (unsigned int), cudaMemcpyDeviceToHost, s->st));
-  int rc = vf_enqueue_segment (h, s, 1, s->d_in, s->d_out_main, s->d_out_raw, -1);
+  int rc = vf_enqueue_segment (h, s, antenna, 1, s->d_in, s->d_out_main, s->d_out_raw, -1);
   if (rc) return rc;
   CK (cudaMemcpyAsync (fb_main, s->d_out_main, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
   if (h->cfg.rfi_mode == 2 && fb_raw)
@@ -637,7 +748,6 @@ int vf_submit_vdif_async (vf_handle *h, int slot, int antenna, const void *frame
   CK (cudaEventRecord (s->ev_done, s->st));
   s->pending = 2;               /* 2: vf_wait also reports frames outside the window */
   s->first_frame = first_frame;
-  h->last_slot = slot;
   return VF_OK;
 }
 
@@ -680,17 +790,17 @@ int vf_process_device (vf_handle *h, int n_ant, int n_seg, const uint8_t *d_in,
   for (int sg = 0, bi = 0; sg < n_seg; sg += nb, ++bi) {
     const int m = n_seg - sg < nb ? n_seg - sg : nb;
     vf_slot *s = &h->slot[h->next_slot];
-    rc = vf_enqueue_segment (h, s, n_ant, d_in + (size_t) sg * in_seg, d_fb_main + (size_t) sg * out_seg,
+    rc = vf_enqueue_segment (h, s, 0, n_ant, d_in + (size_t) sg * in_seg, d_fb_main + (size_t) sg * out_seg,
                              d_fb_raw ? d_fb_raw + (size_t) sg * out_seg : NULL, bi < h->n_timed ? bi : -1, m);
     if (rc) return rc;
-    h->last_slot = h->next_slot;
     h->next_slot ^= 1;
   }
   return vf_timing_end (h);
 }
 
-/* self-check of the packed division used by the normaliser: q_packed from the kernel's own routine,
- * q_ref from CUDA's div.rn.f32, for n (even) host operand pairs p / b */
+#ifdef VF_TESTING
+/* TESTING BUILDS ONLY (libvlitefast_testing.so, csrc/vf_testing.h): self-check of the packed division used by the
+ * normaliser: q_packed from the kernel's own routine, q_ref from CUDA's div.rn.f32, for n (even) host operand pairs */
 int vf_debug_division (vf_handle *h, const float *p, const float *b, float *q_packed, float *q_ref, size_t n)
 {
   if (!h || !p || !b || !q_packed || !q_ref || (n & 1)) return VF_ERR_ARG;
@@ -706,6 +816,7 @@ int vf_debug_division (vf_handle *h, const float *p, const float *b, float *q_pa
   cudaFree (d);
   return VF_OK;
 }
+#endif
 
 /* serial != 0: segments do not overlap (K1 of segment n+1 waits for K2 of segment n), so that the
  * per-kernel times of vf_last_elapsed_ms are pure execution times.  Also set by VF_SERIAL=1. */
@@ -723,6 +834,35 @@ int vf_sync (vf_handle *h)
   CK (cudaStreamSynchronize (h->slot[0].st));
   CK (cudaStreamSynchronize (h->slot[1].st));
   CK (cudaStreamSynchronize (h->coadd_st));
+  return VF_OK;
+}
+
+/* Device-side stopwatch over everything the handle enqueues between the two calls, on all of its streams
+ * (slots and co-add): begin = an event on the control stream that every stream waits for; end = an event on the
+ * control stream after it has joined every stream.  vf_timer_end blocks until that event and returns the time. */
+int vf_timer_begin (vf_handle *h)
+{
+  if (!h) return VF_ERR_ARG;
+  CK (cudaSetDevice (h->cfg.gpu_id));
+  CK (cudaEventRecord (h->ev_u0, h->ctl));
+  CK (cudaStreamWaitEvent (h->slot[0].st, h->ev_u0, 0));
+  CK (cudaStreamWaitEvent (h->slot[1].st, h->ev_u0, 0));
+  CK (cudaStreamWaitEvent (h->coadd_st, h->ev_u0, 0));
+  return VF_OK;
+}
+
+int vf_timer_end (vf_handle *h, float *ms)
+{
+  if (!h || !ms) return VF_ERR_ARG;
+  CK (cudaSetDevice (h->cfg.gpu_id));
+  cudaStream_t sts[3] = { h->slot[0].st, h->slot[1].st, h->coadd_st };
+  for (int i = 0; i < 3; ++i) {
+    CK (cudaEventRecord (h->ev_u1, sts[i]));          /* re-recorded per stream: the wait below captures this record */
+    CK (cudaStreamWaitEvent (h->ctl, h->ev_u1, 0));
+  }
+  CK (cudaEventRecord (h->ev_u1, h->ctl));
+  CK (cudaEventSynchronize (h->ev_u1));
+  CK (cudaEventElapsedTime (ms, h->ev_u0, h->ev_u1));
   return VF_OK;
 }
 
@@ -762,24 +902,25 @@ int vf_get_stats (vf_handle *h, int antenna, float *pw, float *kur, float *dag,
   rc = vf_sync (h);
   if (rc) return rc;
   const size_t nblk = (size_t) h->T * VF_NSUB, T = h->T;
+  const vf_slot *s = &h->slot[h->ant_last[antenna].slot];      /* the slot that processed this antenna last */
   if (pw || kur || dag || pw_fb || kur_fb || dag_fb) {
-    if (!h->pw) return vf_fail (h, VF_ERR_STATE, "statistics need keep_stats and rfi_mode != 0");
-    if (pw) CK (cudaMemcpy (pw, h->pw + (size_t) antenna * 2 * nblk, 2 * nblk * 4, cudaMemcpyDeviceToHost));
-    if (kur) CK (cudaMemcpy (kur, h->kur + (size_t) antenna * 2 * nblk, 2 * nblk * 4, cudaMemcpyDeviceToHost));
-    if (dag) CK (cudaMemcpy (dag, h->dag + (size_t) antenna * 2 * nblk, 2 * nblk * 4, cudaMemcpyDeviceToHost));
-    if (pw_fb) CK (cudaMemcpy (pw_fb, h->pw_fb + (size_t) antenna * 2 * T, 2 * T * 4, cudaMemcpyDeviceToHost));
-    if (kur_fb) CK (cudaMemcpy (kur_fb, h->kur_fb + (size_t) antenna * 2 * T, 2 * T * 4, cudaMemcpyDeviceToHost));
-    if (dag_fb) CK (cudaMemcpy (dag_fb, h->dag_fb + (size_t) antenna * 2 * T, 2 * T * 4, cudaMemcpyDeviceToHost));
+    if (!s->pw) return vf_fail (h, VF_ERR_STATE, "statistics need keep_stats and rfi_mode != 0");
+    if (pw) CK (cudaMemcpy (pw, s->pw + (size_t) antenna * 2 * nblk, 2 * nblk * 4, cudaMemcpyDeviceToHost));
+    if (kur) CK (cudaMemcpy (kur, s->kur + (size_t) antenna * 2 * nblk, 2 * nblk * 4, cudaMemcpyDeviceToHost));
+    if (dag) CK (cudaMemcpy (dag, s->dag + (size_t) antenna * 2 * nblk, 2 * nblk * 4, cudaMemcpyDeviceToHost));
+    if (pw_fb) CK (cudaMemcpy (pw_fb, s->pw_fb + (size_t) antenna * 2 * T, 2 * T * 4, cudaMemcpyDeviceToHost));
+    if (kur_fb) CK (cudaMemcpy (kur_fb, s->kur_fb + (size_t) antenna * 2 * T, 2 * T * 4, cudaMemcpyDeviceToHost));
+    if (dag_fb) CK (cudaMemcpy (dag_fb, s->dag_fb + (size_t) antenna * 2 * T, 2 * T * 4, cudaMemcpyDeviceToHost));
   }
   if (weights) {
     if (!h->cfg.rfi_mode) return vf_fail (h, VF_ERR_STATE, "weights need rfi_mode != 0");
     /* both pols always carry the same weight (src/pb_kernels.cu:132) */
-    CK (cudaMemcpy (weights, h->slot[h->last_slot].w + vf_last_index (h, antenna) * T, T * 4, cudaMemcpyDeviceToHost));
+    CK (cudaMemcpy (weights, s->w + h->ant_last[antenna].idx * T, T * 4, cudaMemcpyDeviceToHost));
     memcpy (weights + T, weights, T * 4);
   }
   if (histo) {
-    if (!h->histo) return vf_fail (h, VF_ERR_STATE, "histogram needs do_histo");
-    CK (cudaMemcpy (histo, h->histo + (size_t) antenna * 512, 512 * 4, cudaMemcpyDeviceToHost));
+    if (!s->histo) return vf_fail (h, VF_ERR_STATE, "histogram needs do_histo");
+    CK (cudaMemcpy (histo, s->histo + (size_t) antenna * 512, 512 * 4, cudaMemcpyDeviceToHost));
   }
   return VF_OK;
 }
@@ -791,7 +932,7 @@ int vf_get_mask (vf_handle *h, int antenna, uint32_t *mask)
   if (!mask) return VF_ERR_ARG;
   rc = vf_sync (h);
   if (rc) return rc;
-  CK (cudaMemcpy (mask, h->slot[h->last_slot].mask + vf_last_index (h, antenna) * h->T, (size_t) h->T * 4, cudaMemcpyDeviceToHost));
+  CK (cudaMemcpy (mask, h->slot[h->ant_last[antenna].slot].mask + h->ant_last[antenna].idx * h->T, (size_t) h->T * 4, cudaMemcpyDeviceToHost));
   return VF_OK;
 }
 
@@ -805,7 +946,7 @@ int vf_get_power_f32 (vf_handle *h, int antenna, int which, float *out)
   rc = vf_sync (h);
   if (rc) return rc;
   const size_t n = (size_t) h->cfg.npol * h->ntime * VF_NCHANOUT;
-  const size_t last = (size_t) ((h->seg_counter + h->ave_nseg - 1) % h->ave_nseg) * h->n_ant * n;
+  const size_t last = (size_t) ((h->ant_seg[antenna] + h->ave_nseg - 1) % h->ave_nseg) * h->n_ant * n;
   CK (cudaMemcpy (out, src + last + (size_t) antenna * n, n * 4, cudaMemcpyDeviceToHost));
   return VF_OK;
 }
@@ -819,10 +960,10 @@ int vf_get_detected_power (vf_handle *h, int antenna, int which, float *out)
   if (which == 1 && mode != 2) return vf_fail (h, VF_ERR_STATE, "raw stream beside the main one needs rfi_mode 2");
   rc = vf_sync (h);
   if (rc) return rc;
-  vf_slot *s = &h->slot[h->last_slot];
-  const size_t n = h->tile_elems, off = vf_last_index (h, antenna) * n;
+  vf_slot *s = &h->slot[h->ant_last[antenna].slot];
+  const size_t n = h->tile_elems, off = h->ant_last[antenna].idx * n;
   const bool want_kur = (which == 0 && mode != 0);
-  /* the device tile is blocked ([4096/16][T][16], VF_PBLK): copy it out and put it in [T][4096] order */
+  /* the device tile is [4096 / VF_PBLK][T][VF_PBLK] (VF_PBLK = 4096: plain [T][4096]): copy it out in [T][4096] order */
   std::vector<float2> blk (n), blk_raw;
   CK (cudaMemcpy (blk.data (), (want_kur ? s->P_kur : s->P_raw) + off, n * sizeof (float2), cudaMemcpyDeviceToHost));
   std::vector<uint32_t> mk;
@@ -830,7 +971,7 @@ int vf_get_detected_power (vf_handle *h, int antenna, int which, float *out)
     /* time steps with an empty mask were not re-transformed: identical to raw */
     mk.resize (h->T);
     blk_raw.resize (n);
-    CK (cudaMemcpy (mk.data (), s->mask + vf_last_index (h, antenna) * h->T, (size_t) h->T * 4, cudaMemcpyDeviceToHost));
+    CK (cudaMemcpy (mk.data (), s->mask + h->ant_last[antenna].idx * h->T, (size_t) h->T * 4, cudaMemcpyDeviceToHost));
     CK (cudaMemcpy (blk_raw.data (), s->P_raw + off, n * sizeof (float2), cudaMemcpyDeviceToHost));
   }
   float2 *o2 = reinterpret_cast<float2 *> (out);
@@ -950,7 +1091,7 @@ int vf_coadd_init (vf_handle *h, int nranks, int rank, const void *nccl_unique_i
   CK (cudaSetDevice (h->cfg.gpu_id));
   const size_t n = (size_t) h->cfg.npol * h->ntime * VF_NCHANOUT;
   if (!h->coadd_sum) {
-    CK (cudaMalloc ((void **) &h->coadd_sum, n * h->ave_nseg * sizeof (float)));
+    CK (cudaMalloc ((void **) &h->coadd_sum, (n + h->ntime) * h->ave_nseg * sizeof (float)));
     CK (cudaMalloc ((void **) &h->coadd_out, n * h->ave_nseg * h->cfg.nbit / 8));
     CK (cudaEventCreateWithFlags (&h->coadd_batch[0].ev, cudaEventDisableTiming));
     CK (cudaEventCreateWithFlags (&h->coadd_batch[1].ev, cudaEventDisableTiming));
@@ -968,41 +1109,48 @@ int vf_coadd_init (vf_handle *h, int nranks, int rank, const void *nccl_unique_i
   return VF_OK;
 }
 
+/* Co-add of the last n_seg segments.  Definition (the reference's co-adder is an external
+ * program whose source is not in the tree): per output sample, the sum over antennas of the main-stream
+ * pre-digitisation values divided by sqrt (number of antennas whose scrunched row was kept), the way
+ * tscrunch_weights (src/pb_kernels.cu:591-630) treats the time steps of a row; 0 when no antenna kept the row.
+ * Values and counts travel in ONE reduce: [n_seg tiles | n_seg x T/8 counts]. */
 int vf_coadd_batch (vf_handle *h, int root, int total_antennas, int n_seg, uint8_t *fb_coadd, float *sum_f32, int wait)
 {
   if (!h || total_antennas < 1 || n_seg < 1) return VF_ERR_ARG;
   if (!h->coadd_sum) return vf_fail (h, VF_ERR_STATE, "vf_coadd_init not called");
-  if (n_seg > h->ave_nseg || n_seg > h->seg_counter)
+  const int na = h->last_n_ant;                 /* antennas of the last launches: their tiles are the current ones */
+  const long seg_end = h->ant_seg[0];
+  for (int a = 1; a < na; ++a)
+    if (h->ant_seg[a] != seg_end) return vf_fail (h, VF_ERR_STATE, "antennas 0 and %d are not at the same segment", a);
+  if (n_seg > h->ave_nseg || n_seg > seg_end)
     return vf_fail (h, VF_ERR_ARG, "n_seg %d exceeds the %d kept tile(s)", n_seg, h->ave_nseg);
   if (root < 0 || root >= (h->nranks ? h->nranks : 1)) return vf_fail (h, VF_ERR_ARG, "bad root");
   CK (cudaSetDevice (h->cfg.gpu_id));
   const size_t n = (size_t) h->cfg.npol * h->ntime * VF_NCHANOUT;        /* one tile */
   const size_t out1 = n * h->cfg.nbit / 8;
+  float *cnt = h->coadd_sum + (size_t) n_seg * n;                        /* [n_seg][T/8] right behind the sums */
   cudaStream_t st = h->coadd_st;
   /* after every K2 that wrote the tiles */
   if (h->have_k2_last) CK (cudaStreamWaitEvent (st, h->ev_k2_last, 0));
-  /* local sum over this handle's antennas, segment by segment in time order */
-  for (int i = 0; i < n_seg; ++i) {
-    const long seg = h->seg_counter - n_seg + i;
-    const float *tiles = h->ave_main + (size_t) (seg % h->ave_nseg) * h->n_ant * n;
-    float *dst = h->coadd_sum + (size_t) i * n;
-    CK (cudaMemcpyAsync (dst, tiles, n * sizeof (float), cudaMemcpyDeviceToDevice, st));
-    for (int a = 1; a < h->n_ant; ++a)
-      CK (vf_launch_accum (dst, tiles + (size_t) a * n, n, st));
+  /* local sum and count over this handle's antennas, the segments of the batch in time order, one launch */
+  {
+    vf_coadd_local_params lp;
+    lp.tiles = h->ave_main; lp.rowok = h->rowok;
+    lp.seg0 = seg_end - n_seg; lp.nring = h->ave_nseg; lp.n_ant_total = h->n_ant;
+    lp.n_ant = na; lp.ntime = h->ntime; lp.npol = h->cfg.npol; lp.n_seg = n_seg;
+    lp.sum = h->coadd_sum; lp.cnt = cnt;
+    CK (vf_launch_coadd_local (lp, st));
   }
   if (h->nranks > 1) {
-    /* ncclFloat32 = 7, ncclSum = 0 (nccl.h); one collective for the whole batch */
-    int e = g_nccl.Reduce (h->coadd_sum, h->coadd_sum, n * n_seg, 7, 0, root, h->comm, st);
+    /* ncclFloat32 = 7, ncclSum = 0 (nccl.h); one collective for the whole batch, sums and counts */
+    int e = g_nccl.Reduce (h->coadd_sum, h->coadd_sum, (n + h->ntime) * n_seg, 7, 0, root, h->comm, st);
     if (e != 0) return vf_fail (h, VF_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString (e) : "?");
   }
   if (h->rank == root) {
-    for (int i = 0; i < n_seg; ++i) {
-      vf_coadd_params cp;
-      cp.sum = h->coadd_sum + (size_t) i * n; cp.cnt = NULL;
-      cp.scale = (float) (1.0 / sqrt ((double) total_antennas));
-      cp.ntime = h->ntime; cp.npol = h->cfg.npol; cp.nbit = h->cfg.nbit; cp.out = h->coadd_out + (size_t) i * out1;
-      CK (vf_launch_coadd (cp, st));
-    }
+    vf_coadd_params cp;
+    cp.sum = h->coadd_sum; cp.cnt = cnt;
+    cp.ntime = h->ntime; cp.npol = h->cfg.npol; cp.nbit = h->cfg.nbit; cp.n_seg = n_seg; cp.out = h->coadd_out;
+    CK (vf_launch_coadd (cp, st));
     if (fb_coadd) CK (cudaMemcpyAsync (fb_coadd, h->coadd_out, out1 * n_seg, cudaMemcpyDeviceToHost, st));
     if (sum_f32) CK (cudaMemcpyAsync (sum_f32, h->coadd_sum, n * n_seg * sizeof (float), cudaMemcpyDeviceToHost, st));
   }
@@ -1011,10 +1159,11 @@ int vf_coadd_batch (vf_handle *h, int root, int total_antennas, int n_seg, uint8
     const int b = h->coadd_next;
     if (h->coadd_batch[b].pending) CK (cudaStreamWaitEvent (st, h->coadd_batch[b].ev, 0));   /* same stream: already ordered */
     CK (cudaEventRecord (h->coadd_batch[b].ev, st));
-    h->coadd_batch[b].lo = h->seg_counter - n_seg; h->coadd_batch[b].hi = h->seg_counter; h->coadd_batch[b].pending = 1;
+    h->coadd_batch[b].lo = seg_end - n_seg; h->coadd_batch[b].hi = seg_end; h->coadd_batch[b].pending = 1;
     h->coadd_next ^= 1;
   }
   if (wait) CK (cudaStreamSynchronize (st));
+  (void) total_antennas;      /* kept in the signature: the count of contributing antennas is reduced with the data */
   return VF_OK;
 }
 

@@ -98,14 +98,22 @@ VF_HD float2 vf_sub2 (float2 a, float2 b) { return vf_add2 (a, make_float2 (-b.x
 VF_HD float2 vf_add_mi (float2 a, float2 u) { return vf_add2 (a, make_float2 (u.y, -u.x)); }
 VF_HD float2 vf_add_pi (float2 a, float2 u) { return vf_add2 (a, make_float2 (-u.y, u.x)); }
 
-/* a b = (a.x b.x - a.y b.y, a.x b.y + a.y b.x): two packed instructions */
+/* a b = (a.x b.x - a.y b.y, a.y b.x + a.x b.y) in exactly two packed instructions and no data movement:
+ *   t = b.y * (a.y, a.x)            FMUL2  t, b.y (scalar), a (halves swapped)
+ *   r = b.x * (a.x, a.y) + (-t.x, t.y)   FFMA2  r, b.x (scalar), a, t (first half negated)
+ * The operand modifiers of the packed instructions (swap of the halves, negation of one half, a scalar
+ * register or an immediate broadcast to both halves) cover every step; written as
+ * fma (bc (a.x), b, mul (bc (a.y), (-b.y, b.x))) the same product costs two more instructions (a MOV and
+ * a negating FADD to build the rotated copy of b).  a is the data, b the twiddle. */
 VF_HD float2 vf_cmul (float2 a, float2 b)
 {
-  return vf_fma2 (vf_bc (a.x), b, vf_mul2 (vf_bc (a.y), make_float2 (-b.y, b.x)));
+  const float2 t = vf_mul2 (vf_bc (b.y), make_float2 (a.y, a.x));
+  return vf_fma2 (vf_bc (b.x), a, make_float2 (-t.x, t.y));
 }
 
-/* v *= (wr + i wi), compile-time constant */
-#define VF_CMULC(v, wr, wi) do { (v) = vf_cmul ((v), make_float2 ((wr), (wi))); } while (0)
+/* v *= (wr + i wi), compile-time constant: both factors are immediates of the two instructions
+ *   t = wi * (-v.y, v.x);  v = wr * v + t */
+#define VF_CMULC(v, wr, wi) do { (v) = vf_fma2 ((v), vf_bc (wr), vf_mul2 (make_float2 (-(v).y, (v).x), vf_bc (wi))); } while (0)
 
 #include "vf_fft_consts.h"
 
@@ -272,8 +280,12 @@ VF_HD void vf_pass2 (int b, const vf_fft_tables &tb, float2 *W)
 }
 
 /* pass 3: butterfly m in [0,625): k1 = m % 25, k2 = m / 25; in place.  Only
- * outputs k = k1 + 25 k2 + 625 k3 in [lo, hi] are stored. */
-VF_HD void vf_pass3 (int m, float2 *W, int lo, int hi)
+ * outputs k = kb + 625 k3 (kb = k1 + 25 k2 < 625) in [LO, HI] are stored.  For a given k3 that is decided at
+ * compile time unless the range boundary falls inside [625 k3, 625 k3 + 624]: with the reference's channels
+ * (LO = CHANMIN = 2155, HI = N - CHANMIN) twelve of the twenty stores are unconditional, two depend on kb and
+ * six (with the additions that feed them) disappear. */
+template <int LO, int HI>
+VF_HD void vf_pass3 (int m, float2 *W)
 {
   const int k2 = m / 25, k1 = m - 25 * k2;
   float2 *o = W + VF_WS * k1 + 20 * k2;
@@ -281,13 +293,15 @@ VF_HD void vf_pass3 (int m, float2 *W, int lo, int hi)
 #pragma unroll
   for (int j = 0; j < 20; ++j) v[j] = o[j];
   vf_dft20 (v);
-  const int kb = k1 + 25 * k2;
+  const int kb = m;                      /* k1 + 25 k2 with k2 = m / 25, k1 = m % 25 */
 #pragma unroll
   for (int d = 0; d < 5; ++d)
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int k3 = 5 * c + d, k = kb + 625 * k3;
-      if (k >= lo && k <= hi) o[k3] = v[c + 4 * d];
+      const int k3 = 5 * c + d, kmin = 625 * k3, kmax = 625 * k3 + 624;
+      if (kmax < LO || kmin > HI) continue;                       /* never needed */
+      if (kmin >= LO && kmax <= HI) o[k3] = v[c + 4 * d];         /* always needed */
+      else if (kb + kmin >= LO && kb + kmin <= HI) o[k3] = v[c + 4 * d];
     }
 }
 

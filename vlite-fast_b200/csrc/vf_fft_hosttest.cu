@@ -40,7 +40,11 @@ int main (int argc, char **argv)
     else vf_pass1<false> (p, b.data (), b.data () + 12500, 0, tb, W.data ());
   }
   for (int i = 0; i < VF_NA; ++i) vf_pass2 (i, tb, W.data ());
-  for (int m = 0; m < VF_NC; ++m) vf_pass3 (m, W.data (), lo, hi);
+  /* the store range is a compile-time parameter of pass 3: everything (tests of the whole spectrum) or the
+   * kernel's range (the channels the filterbank keeps and their mirror images) */
+  if (lo == 0 && hi == 12499) for (int m = 0; m < VF_NC; ++m) vf_pass3<0, 12499> (m, W.data ());
+  else if (lo == 2155 && hi == 10345) for (int m = 0; m < VF_NC; ++m) vf_pass3<2155, 10345> (m, W.data ());
+  else return 3;
   std::vector<float2> P (4096), Z (12500, make_float2 (0.f, 0.f));
   for (int c = 0; c < 4096; ++c) P[c] = vf_detect (c + 2155, W.data ());
   for (int k = lo; k <= hi; ++k) Z[k] = W[vf_zpos (k)];

@@ -42,6 +42,7 @@ struct vf_k1_params {
   unsigned int *histo;        /* optional [n_ant][2][256] */
   vf_fft_tables tb;
   double dagc[5], dagc_fb[5]; /* mu1, A, Z1, Z2, Z3 for N = 500 and N = 12500 */
+  double dag_thresh;          /* DAG_THRESH, src/process_baseband.h:42 */
   const float *wtab;          /* [26] device: k-fold float sum of float(500)/12500 */
   const float *frb_delays;    /* optional [6251]; FRB injection, src/pb_kernels.cu:348-391 */
   int nfft_since_frb;
@@ -63,7 +64,10 @@ struct vf_k2_params {
   size_t out_stride;
   float *ave_main, *ave_raw;  /* optional ring of ave_nseg tiles [n_ant][npol][T/8][4096]; segment seg of the launch goes */
   long ave_seg0; int ave_nseg; size_t ave_seg_elems;   /* to tile (ave_seg0 + seg) % ave_nseg, ave_seg_elems floats apart */
-  int debug;                  /* VF_K2_DEBUG (profiling only): 1 skip fan-out, 2 skip recursion, 4 skip weight division */
+  float *rowok;               /* optional, beside the tile ring: [ave_nseg][n_ant_total][T/8], 1 = the scrunched row of the main
+                                 stream was kept, 0 = zeroed by tscrunch_weights (:622-623); the co-add's count */
+  size_t rowok_seg_elems;
+  double min_weight;          /* MIN_WEIGHT, src/process_baseband.h:45 */
 };
 
 struct vf_depack_params {
@@ -76,19 +80,32 @@ struct vf_depack_params {
   unsigned int *bad;          /* count of frames outside the window */
 };
 
+/* both co-add kernels cover the n_seg segments of a batch in one launch (blockIdx.y = segment of the batch);
+ * segment i of the batch lives in slot (seg0 + i) % nring of the ring of kept tiles */
 struct vf_coadd_params {
-  const float *sum;           /* [npol][T/8][4096] summed tiles */
-  const float *cnt;           /* optional same shape: contributing antennas, else NULL */
-  float scale;                /* 1/sqrt(n_ant) when cnt == NULL */
-  int ntime, npol, nbit;
-  uint8_t *out;
+  const float *sum;           /* [n_seg][npol][T/8][4096] summed tiles */
+  const float *cnt;           /* [n_seg][T/8] antennas that contributed to the row (the same for every channel and pol) */
+  int ntime, npol, nbit, n_seg;
+  uint8_t *out;               /* [n_seg][out bytes] */
+};
+
+/* local part of the co-add: sum of the tiles of this handle's antennas and the count of kept rows */
+struct vf_coadd_local_params {
+  const float *tiles;         /* ring [nring][n_ant_total][npol][T/8][4096] */
+  const float *rowok;         /* ring [nring][n_ant_total][T/8] */
+  long seg0; int nring, n_ant_total;
+  int n_ant, ntime, npol, n_seg;
+  float *sum;                 /* [n_seg][npol][T/8][4096] */
+  float *cnt;                 /* [n_seg][T/8] */
 };
 
 cudaError_t vf_launch_k1 (const vf_k1_params &p, int grid, int threads, cudaStream_t s);
 cudaError_t vf_launch_k2 (const vf_k2_params &p, cudaStream_t s);
 cudaError_t vf_launch_depack (const vf_depack_params &p, cudaStream_t s);
 cudaError_t vf_launch_coadd (const vf_coadd_params &p, cudaStream_t s);
-cudaError_t vf_launch_accum (float *dst, const float *src, size_t n, cudaStream_t s);
+cudaError_t vf_launch_coadd_local (const vf_coadd_local_params &p, cudaStream_t s);
+#ifdef VF_TESTING
 cudaError_t vf_launch_debug_div (const float *p, const float *b, float *q_packed, float *q_ref, size_t n, cudaStream_t s);
+#endif
 size_t vf_k1_smem_bytes (void);
 cudaError_t vf_k1_configure (void);

@@ -1,0 +1,18 @@
+/*
+ * TESTING BUILDS ONLY.  Entry points that exist in libvlitefast_testing.so (the product sources compiled
+ * with -DVF_TESTING) and not in libvlitefast.so: the monolithic channeliser behind vf_config.k1_threads
+ * (320 / 512 / 640) and the self-check below.  tests/ load this library for A/B comparisons only.
+ */
+#ifndef VF_TESTING_H
+#define VF_TESTING_H
+#include "vlitefast.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* the normaliser divides with a packed, branch-free sequence; this runs it beside CUDA's correctly
+ * rounded division on n (even) operand pairs p / b so that a test can compare the bits */
+int vf_debug_division (vf_handle *h, const float *p, const float *b, float *q_packed, float *q_ref, size_t n);
+#ifdef __cplusplus
+}
+#endif
+#endif
