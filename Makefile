@@ -18,7 +18,7 @@ all: $(LIB) $(TESTLIB) $(GENLIB) host oracle build/vf_fft_hosttest scripts/ubenc
 build:
 	mkdir -p build
 
-build/vf_kernels.o: $(CSRC)/vf_kernels.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft12500.cuh $(CSRC)/vf_fft_consts.h | build
+build/vf_kernels.o: $(CSRC)/vf_kernels.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft12500.cuh $(CSRC)/vf_fft_consts.h $(CSRC)/vf_pass3_map.h | build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 build/vf_api.o: $(CSRC)/vf_api.cu $(CSRC)/vf_kernels.h include/vlitefast.h | build
@@ -31,7 +31,7 @@ $(LIB): build/vf_kernels.o build/vf_api.o
 
 # the same sources with -DVF_TESTING: adds the monolithic channeliser (vf_config.k1_threads) and
 # vf_debug_division (csrc/vf_testing.h).  Loaded by tests/ for A/B comparisons only.
-build/vf_kernels_t.o: $(CSRC)/vf_kernels.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft12500.cuh $(CSRC)/vf_fft_consts.h | build
+build/vf_kernels_t.o: $(CSRC)/vf_kernels.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft12500.cuh $(CSRC)/vf_fft_consts.h $(CSRC)/vf_pass3_map.h | build
 	$(NVCC) $(NVFLAGS) -DVF_TESTING -c $< -o $@
 
 build/vf_api_t.o: $(CSRC)/vf_api.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_testing.h include/vlitefast.h | build

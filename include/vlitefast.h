@@ -132,6 +132,18 @@ int vf_wait (vf_handle *h, int slot);
 int vf_submit_vdif_async (vf_handle *h, int slot, int antenna, const void *frames, size_t nframes,
                           uint32_t first_frame, uint8_t *fb_main, uint8_t *fb_raw);
 
+/* The same for a block of n_seg (1..16) consecutive segments -- n_seg = 10: a one-second block of the input ring
+ * (src/process_baseband.cu:1015-1067 places every frame of the second before the ten segments are processed):
+ * one copy, one depacketiser launch over the whole block, ONE launch pair over the n_seg segments; fb_main /
+ * fb_raw receive n_seg x out_bytes.  expect_second >= 0: frames whose VDIF seconds field differs are skipped.
+ * Skipped frames are counted, never fatal: vf_wait returns VF_ERR_VDIF as a warning with the outputs complete
+ * (the gaps are zeros = dropped samples) and vf_vdif_report gives the counts: [0] outside the block, [1] other
+ * second, [2] placed, [3] invalid bit, [4] frames of a complete block.  Needs a handle without keep_stats /
+ * do_histo / inject_frb when n_seg > 1. */
+int vf_submit_vdif_block_async (vf_handle *h, int slot, int antenna, const void *frames, size_t nframes,
+                                uint32_t first_frame, long expect_second, int n_seg, uint8_t *fb_main, uint8_t *fb_raw);
+int vf_vdif_report (vf_handle *h, int slot, unsigned int counts[5]);
+
 /* Device-resident form: d_in is [n_ant][2][ffts_per_seg*12500] bytes on the
  * device (256-byte aligned), d_fb_main / d_fb_raw [n_ant][out_bytes].  Enqueued
  * on the handle's stream; vf_sync waits for it.  n_seg consecutive segments

@@ -141,3 +141,68 @@ def test_output_rings(pkg, tmp_path):
     finally:
         for k in (kout, kco):
             subprocess.run([os.path.join(BIN, "vf_dada_db"), "-k", k, "-d"], stdout=subprocess.DEVNULL)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "process_baseband")), reason="executables not built")
+def test_frames_anywhere_in_the_second_and_statistics_dumps(pkg, tmp_path):
+    """(1) ADVICE r01: the executable hands the whole one-second block to the library, so frames may sit anywhere in
+    the second (the reference places them by header across the second, src/process_baseband.cu:1015-1035); a frame of
+    another second is skipped with a warning, not fatal.  (2) -W / -H: the WRITE_KURTO / DOHISTO dumps
+    (:1378-1393, :1444-1450) next to the filterbank equal vf_get_stats of every segment."""
+    vdif = tmp_path / "one.vdif"
+    subprocess.run([os.path.join(BIN, "genbase"), "-o", str(vdif), "-t", "1", "-r", "13", "-f", "-n", "4"], check=True)
+    frames = np.fromfile(vdif, np.uint8).reshape(-1, 5032).copy()
+    out = {}
+    for tag, extra in (("plain", []), ("dumps", ["-W", "-H", "-T"])):
+        d = tmp_path / tag
+        d.mkdir()
+        r = subprocess.run([os.path.join(BIN, "process_baseband"), "-f", str(vdif), "-D", str(d), "-b", "8", "-r", "2", "-a", "4", "-j", "-n", "2", "-o"] + extra,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[tag] = {f: open(d / f, "rb").read() for f in sorted(os.listdir(d))}
+        if extra:
+            assert "Channelise.." in r.stderr and "Normalise..." in r.stderr
+    fil = [f for f in out["plain"] if f.endswith("_kur.fil")][0]
+    assert out["plain"][fil] == out["dumps"][fil]                     # block path == per-segment path
+    # shuffled across the whole second, one frame re-stamped with another second
+    rng = np.random.default_rng(5)
+    sh = frames[rng.permutation(frames.shape[0])].copy()
+    victim = int(np.flatnonzero((sh[:, 4:8].copy().view(np.uint32)[:, 0] & 0xFFFFFF) == 1234)[0])
+    sec = int(sh[victim, :4].copy().view(np.uint32)[0] & 0x3FFFFFFF)
+    # keep the first frame in place: the executable checks the alignment of the observation's first frame (:843-849)
+    first = int(np.flatnonzero(((sh[:, 4:8].copy().view(np.uint32)[:, 0] & 0xFFFFFF) == 0) & (((sh[:, 12:16].copy().view(np.uint32)[:, 0] >> 16) & 0x3FF) == 0))[0])
+    sh[[0, first]] = sh[[first, 0]]
+    if victim == 0 or victim == first:
+        victim = 7
+    pol = ((sh[victim, 12:16].copy().view(np.uint32)[0] >> 16) & 0x3FF) != 0
+    fno = int(sh[victim, 4:8].copy().view(np.uint32)[0] & 0xFFFFFF)
+    sh[victim, :4] = np.frombuffer(np.uint32(sec + 1).tobytes(), np.uint8)
+    shf = tmp_path / "shuffled.vdif"
+    sh.tofile(shf)
+    d = tmp_path / "shuffled"
+    d.mkdir()
+    r = subprocess.run([os.path.join(BIN, "process_baseband"), "-f", str(shf), "-D", str(d), "-b", "8", "-r", "2", "-a", "4", "-j", "-n", "2", "-o"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "of another second skipped" in r.stderr
+    # the same stream with that frame's samples dropped, through the binding
+    ordered = frames.copy()
+    idx = 2 * fno + int(pol)
+    ordered[idx, 3] |= 0x80                                           # invalid bit: an absent frame
+    with pkg.Pipeline(ffts_per_seg=1024, nbit=8, npol=1, rfi_mode=2) as p:
+        main, raw, rep, warned = p.process_vdif_block(np.ascontiguousarray(ordered).reshape(-1), 0, sec, 10)
+    got = open(d / [f for f in os.listdir(d) if f.endswith("_kur.fil")][0], "rb").read()
+    _, _, used = parse_sigproc(got)
+    assert np.array_equal(np.frombuffer(got[used:], np.uint8), main.reshape(-1))
+    # dumps against the binding, segment by segment
+    base = fil[:-len("_kur.fil")]
+    kur = np.frombuffer(out["dumps"][base + ".kurto"], np.float32).reshape(10, 2 * 1024 * 25)
+    kfb = np.frombuffer(out["dumps"][base + ".block_kurto"], np.float32).reshape(10, 2 * 1024)
+    wts = np.frombuffer(out["dumps"][base + ".weights"], np.float32).reshape(10, 1024)
+    his = np.frombuffer(out["dumps"][base + ".histo"], np.uint32).reshape(10, 512)
+    with pkg.Pipeline(ffts_per_seg=1024, nbit=8, npol=1, rfi_mode=2, keep_stats=1, do_histo=1) as p:
+        for s in range(10):
+            p.process_vdif(np.ascontiguousarray(frames[s * 5120:(s + 1) * 5120]).reshape(-1), s * 2560)
+            st = p.get_stats()
+            assert np.array_equal(st["kur"], kur[s], equal_nan=True) and np.array_equal(st["kur_fb"], kfb[s], equal_nan=True), s
+            assert np.array_equal(st["weights"][:1024], wts[s]) and np.array_equal(st["histo"], his[s]), s

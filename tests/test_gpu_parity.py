@@ -544,19 +544,68 @@ def test_coadd_sums_only_the_antennas_of_the_last_launch(pkg, orc):
 
 def test_thresholds_are_configurable(pkg):
     """dag_thresh / min_weight (DAG_THRESH, MIN_WEIGHT of src/process_baseband.h:42,45) are carried by vf_config"""
-    T = 32
+    T = 128
     p0, p1 = make_input(pkg, T, seed=14, **RFI)
-    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=1, keep_stats=1) as p:
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=1, keep_stats=1, keep_power=1) as p:
         p.process_segment(p0, p1)
         dag, m_def = p.get_stats()["dag"][:T * 25].reshape(T, 25), p.get_mask()
-    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=1, keep_stats=1, dag_thresh=1.5, min_weight=0.9, keep_power=1) as p:
-        p.process_segment(p0, p1)
-        m, w = p.get_mask(), p.get_stats()["weights"][:T]
-        ave = p.get_power_f32(0, 0)
-    want = ((dag > np.float32(1.5)).astype(np.uint32) << np.arange(25, dtype=np.uint32)).sum(axis=1).astype(np.uint32)
-    assert np.array_equal(m, want) and not np.array_equal(m, m_def)
-    kept = _row_kept(w, 0.9)
-    assert 0 < kept.sum() < kept.size                        # the test input must exercise both outcomes
-    assert np.all(ave[0, ~kept] == 0) and np.all(np.abs(ave[0, kept]).max(axis=1) > 0)
+        zero_def = np.all(p.get_power_f32(0, 0)[0] == 0, axis=1)
+    outcomes = set()
+    for thr, mw in ((2.0, 0.5), (1.5, 0.8), (1.0, 0.9)):
+        with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=1, keep_stats=1, dag_thresh=thr, min_weight=mw, keep_power=1) as p:
+            p.process_segment(p0, p1)
+            m, w = p.get_mask(), p.get_stats()["weights"][:T]
+            ave = p.get_power_f32(0, 0)
+        want = ((dag > np.float32(thr)).astype(np.uint32) << np.arange(25, dtype=np.uint32)).sum(axis=1).astype(np.uint32)
+        assert np.array_equal(m, want) and not np.array_equal(m, m_def)
+        kept = _row_kept(w, mw)
+        assert np.array_equal(np.all(ave[0] == 0, axis=1), ~kept), (thr, mw)
+        outcomes.add((bool(kept.any()), bool((~kept).any())))
+    assert not zero_def.all()
+    assert any(o[1] for o in outcomes)                       # some setting zeroes rows the defaults keep
     with pytest.raises(pkg.VfError):
         pkg.Pipeline(ffts_per_seg=T, dag_thresh=-1.0)
+
+
+def test_vdif_block_places_frames_across_the_whole_block(pkg):
+    """ADVICE r01 / src/process_baseband.cu:1015-1035: every frame of the block is placed by (thread, frame number)
+    wherever it sits in the buffer; a frame of another second is skipped and counted, an absent frame leaves zeros
+    (dropped samples); none of that is fatal, and the block goes through ONE launch pair"""
+    T, nseg = 16, 5
+    per_seg = T * 12500 // 5000                          # frames per pol per segment
+    nfr = per_seg * nseg
+    g = pkg.GenParams.default(seed=17, **RFI)
+    sec, first = 4321, 800
+    frames = pkg.gen_vdif_second(g, 0, sec, first, nfr).reshape(-1, 5032).copy()
+    s0 = (sec * 25600 + first) * 5000
+    p0 = pkg.gen_samples(g, 0, 0, s0, nseg * T * 12500).copy()
+    p1 = pkg.gen_samples(g, 0, 1, s0, nseg * T * 12500).copy()
+    # frame 50 of thread 0 is absent, frame 120 of thread 1 carries another second, frame 130 (both threads) the invalid bit
+    keep = np.ones(frames.shape[0], bool)
+    keep[2 * 50] = False
+    frames[2 * 120 + 1, :4] = np.frombuffer(np.uint32(sec + 1).tobytes(), np.uint8)
+    frames[2 * 130, 3] |= 0x80; frames[2 * 130 + 1, 3] |= 0x80
+    p0[50 * 5000:51 * 5000] = 0
+    p1[120 * 5000:121 * 5000] = 0
+    p0[130 * 5000:131 * 5000] = 0; p1[130 * 5000:131 * 5000] = 0
+    fr = frames[keep]
+    perm = np.random.default_rng(1).permutation(fr.shape[0])        # any order across the WHOLE block
+    shuffled = np.ascontiguousarray(fr[perm]).reshape(-1)
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2) as p:
+        want = [p.process_segment(p0[s * T * 12500:(s + 1) * T * 12500], p1[s * T * 12500:(s + 1) * T * 12500]) for s in range(nseg)]
+        wmask = p.get_mask()
+        p.reset_bandpass()
+        main, raw, rep, warned = p.process_vdif_block(shuffled, first, sec, nseg)
+        assert warned and rep == (0, 1, 2 * nfr - 4, 2, 2 * nfr)
+        assert np.array_equal(p.get_mask(), wmask)
+        for s in range(nseg):
+            assert np.array_equal(main[s], want[s][0]) and np.array_equal(raw[s], want[s][1]), s
+        # a clean block: no warning
+        p.reset_bandpass()
+        clean = pkg.gen_vdif_second(g, 0, sec, first, nfr)
+        _, _, rep, warned = p.process_vdif_block(clean, first, sec, nseg, slot=1)
+        assert not warned and rep == (0, 0, 2 * nfr, 0, 2 * nfr)
+    with pkg.Pipeline(ffts_per_seg=T, nbit=8, rfi_mode=2, keep_stats=1) as p:
+        with pytest.raises(pkg.VfError) as e:                      # statistics dumps are per segment
+            p.process_vdif_block(clean, first, sec, nseg)
+        assert e.value.code == 22

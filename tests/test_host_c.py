@@ -341,3 +341,13 @@ def test_dada_db_and_genbase_into_ring(H, pkg, tmp_path):
     finally:
         subprocess.run([os.path.join(BIN, "vf_dada_db"), "-k", "%x" % key, "-d"], check=True, stdout=subprocess.DEVNULL)
     assert not H.vf_ring_connect_shm(key)
+
+
+def test_psrdada_backed_ring_type_checks():
+    """the ring surface of process_baseband on psrdada's own calls (host/psrdada/vf_ring_psrdada.c)
+    compiles against headers carrying psrdada's prototypes (compile-only: psrdada is not in the image)"""
+    import subprocess
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "vlite-fast_b200", "host"), "psrdada-check", "HOSTCC=/usr/bin/gcc"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "warning" not in r.stdout

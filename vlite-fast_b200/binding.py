@@ -66,6 +66,8 @@ def lib(testing=False):
     L.vf_submit_async.argtypes = [vp, i, i, pp, pp, sz, pp, pp]
     L.vf_wait.argtypes = [vp, i]
     L.vf_submit_vdif_async.argtypes = [vp, i, i, vp, sz, C.c_uint32, u8p, u8p]
+    L.vf_submit_vdif_block_async.argtypes = [vp, i, i, vp, sz, C.c_uint32, C.c_long, i, u8p, u8p]
+    L.vf_vdif_report.argtypes = [vp, i, C.POINTER(C.c_uint * 5)]
     L.vf_process_device.argtypes = [vp, i, i, vp, vp, vp]
     L.vf_sync.argtypes = [vp]
     L.vf_set_serial.argtypes = [vp, i]
@@ -249,6 +251,20 @@ class Pipeline:
         self._ck(self.L.vf_process_vdif(self.h, antenna, _ptr(frames), frames.size // VD_FRM, first_frame,
                                         _ptr(main), _ptr(raw), C.byref(nb)))
         return main, raw
+
+    def process_vdif_block(self, frames, first_frame, expect_second, n_seg, antenna=0, slot=0):
+        """vf_submit_vdif_block_async + vf_wait: returns (fb_main [n_seg][out_bytes], fb_raw or None, report, warned);
+        report = (outside the block, other second, placed, invalid bit, frames of a complete block)"""
+        main = np.empty((n_seg, self.out_bytes), np.uint8)
+        raw = np.empty((n_seg, self.out_bytes), np.uint8) if self.cfg.rfi_mode == 2 else None
+        self._ck(self.L.vf_submit_vdif_block_async(self.h, slot, antenna, _ptr(frames), frames.size // VD_FRM, first_frame,
+                                                   expect_second, n_seg, _ptr(main), _ptr(raw)))
+        rc = self.L.vf_wait(self.h, slot)
+        if rc not in (0, 23):
+            self._ck(rc)
+        rep = (C.c_uint * 5)()
+        self._ck(self.L.vf_vdif_report(self.h, slot, C.byref(rep)))
+        return main, raw, tuple(rep), rc == 23
 
     def process_device(self, n_ant, n_seg, d_in, d_main, d_raw=None):
         """device pointers (ints); asynchronous, see sync()."""

@@ -42,8 +42,12 @@ struct vf_slot {
   uint8_t *d_out_main, *d_out_raw;   /* [n_ant][out_bytes] */
   cudaEvent_t ev_k2, ev_done;
   int pending;                /* vf_submit_*_async issued, vf_wait not yet called */
-  unsigned int *d_bad, *h_bad;/* frames outside the window (VDIF input) */
+  unsigned int *d_bad, *h_bad;/* VDIF input: [0] frames outside the window, [1] frames of another second, [2] frames placed, [3] invalid-bit frames */
   uint32_t first_frame;
+  uint8_t *d_in_blk;          /* depacketised samples of a block of segments (vf_submit_vdif_block_async), lazily allocated */
+  uint8_t *d_out_blk[2];      /* its packed outputs (main, raw) */
+  int blk_cap;                /* segments those buffers hold */
+  size_t blk_expected;        /* frames a complete block has */
   unsigned int *d_work;       /* item counter of the pipelined channeliser; never reset: */
   unsigned int work_base;     /* its value when the next launch starts                   */
   /* statistics dumps of the segment this slot processed last (keep_stats / do_histo): one set per slot,
@@ -247,6 +251,7 @@ int vf_destroy (vf_handle *h)
     cudaFree (s->d_in); cudaFree (s->d_frames); cudaFree (s->P_raw); cudaFree (s->P_kur);
     cudaFree (s->w); cudaFree (s->mask); cudaFree (s->d_out_main); cudaFree (s->d_out_raw);
     cudaFree (s->d_bad); if (s->h_bad) cudaFreeHost (s->h_bad);
+    cudaFree (s->d_in_blk); cudaFree (s->d_out_blk[0]); cudaFree (s->d_out_blk[1]);
     cudaFree (s->d_work);
     cudaFree (s->pw); cudaFree (s->pw_fb); cudaFree (s->histo);
     if (s->ev_k2) cudaEventDestroy (s->ev_k2);
@@ -492,8 +497,11 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int ant0, int n_ant, co
   k1.pol_stride = h->nsamp;
   k1.ant_stride = 2 * h->nsamp;
   k1.T = h->T; k1.n_ant = n_ant * n_seg; k1.rfi_mode = c.rfi_mode;   /* (segment, antenna) pairs are the channeliser's antennas */
-  k1.P_raw = s->P_raw; k1.P_kur = s->P_kur;
-  k1.w = s->w; k1.mask = s->mask;
+  /* place of this launch in the slot's tile / weight / mask buffers: single-segment launches of a part of the
+   * antennas sit at their handle index, so that the getters find every antenna's last segment */
+  const size_t base = (n_seg == 1) ? (size_t) ant0 : 0;      /* a batched launch fills the buffers from the start */
+  k1.P_raw = s->P_raw ? s->P_raw + base * h->tile_elems : NULL; k1.P_kur = s->P_kur ? s->P_kur + base * h->tile_elems : NULL;
+  k1.w = s->w + base * h->T; k1.mask = s->mask + base * h->T;
   if (s->pw) {
     k1.pw = s->pw + (size_t) ant0 * 2 * nblk; k1.kur = s->kur + (size_t) ant0 * 2 * nblk; k1.dag = s->dag + (size_t) ant0 * 2 * nblk;
     k1.pw_fb = s->pw_fb + (size_t) ant0 * 2 * h->T; k1.kur_fb = s->kur_fb + (size_t) ant0 * 2 * h->T;
@@ -539,7 +547,7 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int ant0, int n_ant, co
   }
   vf_k2_params k2;
   memset (&k2, 0, sizeof (k2));
-  k2.P_raw = s->P_raw; k2.P_kur = s->P_kur; k2.w = s->w; k2.mask = s->mask;
+  k2.P_raw = k1.P_raw; k2.P_kur = k1.P_kur; k2.w = k1.w; k2.mask = k1.mask;
   k2.bp_raw = h->bp_raw + (size_t) ant0 * VF_NCHANOUT;
   k2.bp_kur = ((c.rfi_mode == 2) ? h->bp_kur : h->bp_raw) + (size_t) ant0 * VF_NCHANOUT;
   k2.T = h->T; k2.n_ant = n_ant; k2.n_seg = n_seg; k2.rfi_mode = c.rfi_mode; k2.npol = c.npol; k2.nbit = c.nbit;
@@ -559,7 +567,7 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int ant0, int n_ant, co
     for (int a = 0; a < n_ant; ++a) {
       h->ant_seg[ant0 + a] = seg0 + n_seg;
       h->ant_last[ant0 + a].slot = (int) (s - h->slot);
-      h->ant_last[ant0 + a].idx = (size_t) (n_seg - 1) * n_ant + a;
+      h->ant_last[ant0 + a].idx = base + (size_t) (n_seg - 1) * n_ant + a;
     }
     h->last_n_ant = n_ant;
   }
@@ -645,8 +653,9 @@ int vf_wait (vf_handle *h, int slot)
   const int kind = s->pending;
   s->pending = 0;
   CK (cudaEventSynchronize (s->ev_done));
-  if (kind == 2 && *s->h_bad)
-    return vf_fail (h, VF_ERR_VDIF, "%u frame(s) outside the segment starting at frame %u", *s->h_bad, s->first_frame);
+  if (kind == 2 && (s->h_bad[0] || s->h_bad[1]))
+    return vf_fail (h, VF_ERR_VDIF, "%u frame(s) outside the block starting at frame %u, %u of another second: skipped (outputs complete)",
+                    s->h_bad[0], s->first_frame, s->h_bad[1]);
   return VF_OK;
 }
 
@@ -708,46 +717,97 @@ int vf_process_segment (vf_handle *h, int antenna,
   return rc;
 }
 
-int vf_submit_vdif_async (vf_handle *h, int slot, int antenna, const void *frames, size_t nframes,
-                          uint32_t first_frame, uint8_t *fb_main, uint8_t *fb_raw)
+/* Frames of n_seg consecutive segments of one antenna (n_seg = 10: a one-second block of the input ring), in any
+ * order: one copy, one depacketiser launch that places every frame by (thread id, frame number) across the whole
+ * block -- as the reference's host loop does across the second, src/process_baseband.cu:1015-1035 -- and ONE
+ * launch pair over the n_seg segments.  Frames the stream lacks stay zero = dropped samples (the writer's fill
+ * frames, src/writer.c:362,674-687); frames that belong to another second (expect_second >= 0) or fall outside
+ * the block are skipped and counted, never fatal: vf_wait returns VF_ERR_VDIF as a WARNING with the outputs
+ * complete, vf_vdif_report gives the counts. */
+static int vf_submit_vdif_common (vf_handle *h, int slot, int antenna, const void *frames, size_t nframes,
+                                  uint32_t first_frame, long expect_second, int n_seg, uint8_t *fb_main, uint8_t *fb_raw)
 {
   if (!h || !frames || !fb_main) return VF_ERR_ARG;
   if (slot < 0 || slot > 1) return vf_fail (h, VF_ERR_ARG, "bad slot");
   if (antenna < 0 || antenna >= h->n_ant) return vf_fail (h, VF_ERR_ARG, "antenna %d outside 0..%d", antenna, h->n_ant - 1);
+  if (n_seg < 1 || n_seg > 16) return vf_fail (h, VF_ERR_ARG, "n_seg %d outside 1..16", n_seg);
   const size_t per_pol = h->nsamp / VF_VD_DAT;            /* frames per pol per segment */
-  if (nframes > 4 * per_pol) return vf_fail (h, VF_ERR_ARG, "%zu frames for a segment of %zu", nframes, 2 * per_pol);
+  if (h->nsamp % VF_VD_DAT) return vf_fail (h, VF_ERR_ARG, "the VDIF entry points need segments of whole frames (ffts_per_seg a multiple of 2)");
+  if (nframes > 4 * per_pol * n_seg) return vf_fail (h, VF_ERR_ARG, "%zu frames for %d segment(s) of %zu", nframes, n_seg, 2 * per_pol);
   vf_slot *s = &h->slot[slot];
   if (s->pending) return vf_fail (h, VF_ERR_STATE, "slot %d submitted twice without vf_wait", slot);
   CK (cudaSetDevice (h->cfg.gpu_id));
   const size_t bytes = nframes * VF_VD_FRM;
   if (s->frames_cap < bytes) {
     cudaFree (s->d_frames); s->d_frames = NULL; s->frames_cap = 0;
-    size_t cap = bytes > 2 * per_pol * VF_VD_FRM ? bytes : 2 * per_pol * VF_VD_FRM;
+    size_t cap = bytes > 2 * per_pol * n_seg * VF_VD_FRM ? bytes : 2 * per_pol * n_seg * VF_VD_FRM;
     CK (cudaMalloc ((void **) &s->d_frames, cap));
     s->frames_cap = cap;
   }
   if (!s->d_bad) {
-    CK (cudaMalloc ((void **) &s->d_bad, sizeof (unsigned int)));
-    CK (cudaMallocHost ((void **) &s->h_bad, sizeof (unsigned int)));
+    CK (cudaMalloc ((void **) &s->d_bad, 4 * sizeof (unsigned int)));
+    CK (cudaMallocHost ((void **) &s->h_bad, 4 * sizeof (unsigned int)));
+  }
+  uint8_t *d_in = s->d_in, *d_main = s->d_out_main, *d_raw = s->d_out_raw;
+  if (n_seg > 1) {
+    /* statistics dumps, histogram and FRB injection are per segment (vf_max_batch) */
+    if (vf_max_batch (h) < n_seg) return vf_fail (h, VF_ERR_STATE, "blocks of %d segments need a handle without keep_stats / do_histo / inject_frb", n_seg);
+    int rc = vf_ensure_batch (h, n_seg);
+    if (rc) return rc;
+    if (s->blk_cap < n_seg) {
+      cudaFree (s->d_in_blk); cudaFree (s->d_out_blk[0]); cudaFree (s->d_out_blk[1]);
+      s->d_in_blk = NULL; s->d_out_blk[0] = s->d_out_blk[1] = NULL; s->blk_cap = 0;
+      CK (cudaMalloc ((void **) &s->d_in_blk, (size_t) n_seg * 2 * h->nsamp));
+      CK (cudaMalloc ((void **) &s->d_out_blk[0], (size_t) n_seg * h->out_bytes));
+      if (h->cfg.rfi_mode == 2) CK (cudaMalloc ((void **) &s->d_out_blk[1], (size_t) n_seg * h->out_bytes));
+      s->blk_cap = n_seg;
+    }
+    d_in = s->d_in_blk; d_main = s->d_out_blk[0]; d_raw = s->d_out_blk[1];
   }
   CK (cudaMemcpyAsync (s->d_frames, frames, bytes, cudaMemcpyHostToDevice, s->st));
-  /* frames the writer never delivered stay zero, i.e. "dropped" samples
-   * (src/writer.c:362,674-687; byte 0 -> 0.0, src/pb_kernels.cu:28-29) */
-  CK (cudaMemsetAsync (s->d_in, 0, 2 * h->nsamp, s->st));
-  CK (cudaMemsetAsync (s->d_bad, 0, sizeof (unsigned int), s->st));
+  CK (cudaMemsetAsync (d_in, 0, (size_t) n_seg * 2 * h->nsamp, s->st));
+  CK (cudaMemsetAsync (s->d_bad, 0, 4 * sizeof (unsigned int), s->st));
   vf_depack_params dp;
-  dp.frames = s->d_frames; dp.nframes = nframes; dp.out = s->d_in; dp.pol_stride = h->nsamp;
-  dp.frame0 = first_frame; dp.nframes_per_pol = (long long) per_pol; dp.bad = s->d_bad;
+  dp.frames = s->d_frames; dp.nframes = nframes; dp.out = d_in; dp.pol_stride = h->nsamp;
+  dp.seg_stride = 2 * h->nsamp; dp.frames_per_seg = (long long) per_pol;
+  dp.frame0 = first_frame; dp.nframes_per_pol = (long long) per_pol * n_seg; dp.expect_second = expect_second; dp.bad = s->d_bad;
   CK (vf_launch_depack (dp, s->st));
-  CK (cudaMemcpyAsync (s->h_bad, s->d_bad, sizeof (unsigned int), cudaMemcpyDeviceToHost, s->st));
-  int rc = vf_enqueue_segment (h, s, antenna, 1, s->d_in, s->d_out_main, s->d_out_raw, -1);
+  CK (cudaMemcpyAsync (s->h_bad, s->d_bad, 4 * sizeof (unsigned int), cudaMemcpyDeviceToHost, s->st));
+  int rc = vf_enqueue_segment (h, s, antenna, 1, d_in, d_main, d_raw, -1, n_seg);
   if (rc) return rc;
-  CK (cudaMemcpyAsync (fb_main, s->d_out_main, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
+  CK (cudaMemcpyAsync (fb_main, d_main, (size_t) n_seg * h->out_bytes, cudaMemcpyDeviceToHost, s->st));
   if (h->cfg.rfi_mode == 2 && fb_raw)
-    CK (cudaMemcpyAsync (fb_raw, s->d_out_raw, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
+    CK (cudaMemcpyAsync (fb_raw, d_raw, (size_t) n_seg * h->out_bytes, cudaMemcpyDeviceToHost, s->st));
   CK (cudaEventRecord (s->ev_done, s->st));
-  s->pending = 2;               /* 2: vf_wait also reports frames outside the window */
+  s->pending = 2;               /* 2: vf_wait also reports frames that were skipped */
   s->first_frame = first_frame;
+  s->blk_expected = 2 * per_pol * n_seg;
+  return VF_OK;
+}
+
+int vf_submit_vdif_async (vf_handle *h, int slot, int antenna, const void *frames, size_t nframes,
+                          uint32_t first_frame, uint8_t *fb_main, uint8_t *fb_raw)
+{
+  return vf_submit_vdif_common (h, slot, antenna, frames, nframes, first_frame, -1, 1, fb_main, fb_raw);
+}
+
+int vf_submit_vdif_block_async (vf_handle *h, int slot, int antenna, const void *frames, size_t nframes,
+                                uint32_t first_frame, long expect_second, int n_seg, uint8_t *fb_main, uint8_t *fb_raw)
+{
+  return vf_submit_vdif_common (h, slot, antenna, frames, nframes, first_frame, expect_second, n_seg, fb_main, fb_raw);
+}
+
+/* what the depacketiser of the last VDIF submission on `slot` saw (valid after vf_wait):
+ * counts[0] frames outside the block, [1] frames of another second, [2] frames placed, [3] frames with the invalid
+ * bit, [4] frames a complete block has */
+int vf_vdif_report (vf_handle *h, int slot, unsigned int counts[5])
+{
+  if (!h || slot < 0 || slot > 1 || !counts) return VF_ERR_ARG;
+  vf_slot *s = &h->slot[slot];
+  if (!s->h_bad) return vf_fail (h, VF_ERR_STATE, "no VDIF submission on slot %d yet", slot);
+  if (s->pending) return vf_fail (h, VF_ERR_STATE, "slot %d not waited for", slot);
+  for (int i = 0; i < 4; ++i) counts[i] = s->h_bad[i];
+  counts[4] = (unsigned int) s->blk_expected;
   return VF_OK;
 }
 

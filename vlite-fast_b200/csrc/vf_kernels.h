@@ -75,9 +75,12 @@ struct vf_depack_params {
   size_t nframes;
   uint8_t *out;               /* [2][T*12500] */
   size_t pol_stride;
+  size_t seg_stride;          /* out is [segment][2][T*12500]: bytes from one segment to the next */
+  long long frames_per_seg;   /* frames per pol per segment */
   long long frame0;           /* frame number (within second) of sample 0 of out */
-  long long nframes_per_pol;  /* frames that fit in out */
-  unsigned int *bad;          /* count of frames outside the window */
+  long long nframes_per_pol;  /* frames that fit in out (all segments) */
+  long expect_second;         /* VDIF seconds field every frame must carry, < 0 = not checked */
+  unsigned int *bad;          /* [0] outside the window, [1] another second, [2] placed, [3] invalid bit */
 };
 
 /* both co-add kernels cover the n_seg segments of a batch in one launch (blockIdx.y = segment of the batch);

@@ -92,6 +92,12 @@ static void usage (void)
     "  -P NPOL   1 (summed) or 2 polarisations [1]\n"
     "  -r MODE   RFI excision: 0 off, 1 excised stream only, 2 both streams [2]\n"
     "  -i        inject a DM 80 FRB every 60 s\n"
+    "  -R        keep the running bandpass from one observation to the next, as the reference does\n"
+    "            (src/process_baseband.cu:700-709); default: every observation starts from its own mean\n"
+    "  -W        WRITE_KURTO: dump kurtosis, block kurtosis and weights of every segment beside the filterbank\n"
+    "            (.kurto, .block_kurto, .weights; src/process_baseband.cu:1385-1393,1446-1450)\n"
+    "  -H        DOHISTO: dump the per-polarisation sample histograms of every segment (.histo, :1378-1383,1444)\n"
+    "  -T        print per-stage device times at the end of every observation (PROFILE, :1538-1558)\n"
     "  -s        process a single observation then quit\n"
     "  -g GPU    CUDA device [0]\n"
     "  -o        log to stderr as well\n"
@@ -229,6 +235,7 @@ int main (int argc, char **argv)
 {
   const char *file = NULL, *datadir = ".", *logfile = NULL;
   int synth_n = 0, loops = 1, station = 1, nbuf = 0, write_fb = 1, single = 0, json = 0, rfi_flag = 0;
+  int keep_bandpass = 0, profile = 0;
   long shm_key = -1, key_out = 0, key_co = 0;                       /* :344-345 */
   unsigned long long seed = 102;
   vf_config cfg;
@@ -236,7 +243,7 @@ int main (int argc, char **argv)
   int c;
   char mc_group[64] = "";
   int mc_port = VF_MC_READER_PORT, mc_sock = -1;
-  while ((c = getopt (argc, argv, "hf:S:L:e:Fa:n:D:w:b:P:r:isg:ol:jk:K:C:p:m:")) != -1) {
+  while ((c = getopt (argc, argv, "hf:S:L:e:Fa:n:D:w:b:P:r:isg:ol:jk:K:C:p:m:RWHT")) != -1) {
     switch (c) {
       case 'h': usage (); return 0;
       case 'f': file = optarg; break;
@@ -258,6 +265,10 @@ int main (int argc, char **argv)
         if (cfg.rfi_mode < 0 || cfg.rfi_mode > 2) { fprintf (stderr, "Unsupported RFI mode!\n"); return 1; }
         break;
       case 'i': cfg.inject_frb = 1; break;
+      case 'R': keep_bandpass = 1; break;
+      case 'W': cfg.keep_stats = 1; break;                          /* WRITE_KURTO, src/process_baseband.h:48 */
+      case 'H': cfg.do_histo = 1; break;                            /* DOHISTO, :47 */
+      case 'T': profile = 1; break;
       case 's': single = 1; break;
       case 'g': cfg.gpu_id = atoi (optarg); break;
       case 'o': g_stdout = 1; break;
@@ -320,10 +331,24 @@ int main (int argc, char **argv)
   /* 10 s of main-stream output, flushed to the heimdall ring once full and second by second after that (:692-697) */
   const int out_buf_sec = 10;
   uint8_t *out10 = ring_out ? (uint8_t *) malloc ((size_t) out_buf_sec * SEG_PER_SEC * out_bytes) : NULL;
+  /* Statistics dumps, histogram and FRB injection are per segment (the library keeps one launch pair per segment
+   * for them): the per-segment path.  Otherwise a whole one-second block goes to the library at once: one copy,
+   * one depacketiser launch over the second, one launch pair over its ten segments. */
+  const int per_segment = cfg.keep_stats || cfg.do_histo || cfg.inject_frb;
+  const int seg_per_submit = per_segment ? 1 : SEG_PER_SEC;
   uint8_t *obuf[2][2] = {{NULL, NULL}, {NULL, NULL}};             /* [slot][main, raw] pinned */
   for (int s = 0; s < 2; ++s)
     for (int k = 0; k < 2; ++k)
-      if (vf_host_alloc ((void **) &obuf[s][k], out_bytes)) return 21;
+      if (vf_host_alloc ((void **) &obuf[s][k], (size_t) seg_per_submit * out_bytes)) return 21;
+  const int T = cfg.ffts_per_seg;
+  float *st_kur = NULL, *st_kur_fb = NULL, *st_w = NULL;
+  uint32_t *st_histo = NULL;
+  if (cfg.keep_stats) {
+    st_kur = (float *) malloc (sizeof (float) * 2 * (size_t) T * 25);
+    st_kur_fb = (float *) malloc (sizeof (float) * 2 * (size_t) T);
+    st_w = (float *) malloc (sizeof (float) * 2 * (size_t) T);
+  }
+  if (cfg.do_histo) st_histo = (uint32_t *) malloc (sizeof (uint32_t) * 512);
 
   if (synth_n > 0) {
     /* templates straight into the ring blocks (not timed) */
@@ -369,10 +394,53 @@ int main (int argc, char **argv)
     long seconds_done = 0, seg_counter = 0;
     int first = 1, aborted = 0;
     int pend_slot[2] = {0, 0};
+    long pend_sec[2] = {0, 0};
     int blocks_open = 0;
     out_sinks sinks = { ring_out, ring_co, out10, out_bytes, 0, out_buf_sec };
-    vf_reset_bandpass (h, -1);    /* the reference keeps the bandpass across observations (:700-709); a new
-                                     stream here is a new antenna-time, so start clean */
+    FILE *kurto_fp = NULL, *block_kurto_fp = NULL, *weight_fp = NULL, *histo_fp = NULL;
+    double dev_ms = 0, k1_ms = 0, k2_ms = 0, wait_s = 0, write_s = 0;
+    long skipped_frames = 0, missing_frames = 0;
+    if (!keep_bandpass)
+      vf_reset_bandpass (h, -1);  /* the reference keeps the bandpass across observations (:700-709, flag -R); a new
+                                     stream here is by default a new antenna-time and starts from its own mean */
+
+    /* one finished submission (a segment or a block of ten): wait, report skipped frames, write the outputs */
+#define FINISH_SLOT(slot) do { \
+      const double tw0_ = now_s (); \
+      rc = vf_wait (h, (slot)); \
+      wait_s += now_s () - tw0_; \
+      pend_slot[(slot)] = 0; \
+      if (rc == VF_ERR_VDIF) { \
+        /* frames of another second or outside the block were skipped, their samples stay zero (dropped data): \
+         * log and go on, as the reference goes on over the writer's fill frames (src/writer.c:674-687) */ \
+        unsigned int cnt_[5]; \
+        if (vf_vdif_report (h, (slot), cnt_) == VF_OK) { \
+          skipped_frames += cnt_[0] + cnt_[1]; \
+          logmsg ("WARN", "second %ld: %u frame(s) outside the block, %u of another second skipped; %u of %u placed\n", \
+                  pend_sec[(slot)], cnt_[0], cnt_[1], cnt_[2], cnt_[4]); \
+        } \
+        rc = VF_OK; \
+      } \
+      if (rc) { logmsg ("ERR", "segment failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; break; } \
+      { unsigned int cnt_[5]; if (vf_vdif_report (h, (slot), cnt_) == VF_OK && cnt_[2] < cnt_[4]) missing_frames += cnt_[4] - cnt_[2]; } \
+      if (profile) { float a_ = 0, b_ = 0, c_ = 0; if (vf_last_elapsed_ms (h, &a_, &b_, &c_) == VF_OK) { dev_ms += a_; k1_ms += b_; k2_ms += c_; } } \
+      const double tf0_ = now_s (); \
+      if (fb_main) fwrite (obuf[(slot)][0], 1, (size_t) seg_per_submit * out_bytes, fb_main);     /* :1438-1441 */ \
+      if (fb_raw) fwrite (obuf[(slot)][1], 1, (size_t) seg_per_submit * out_bytes, fb_raw); \
+      for (int q_ = 0; q_ < seg_per_submit && !aborted; ++q_) \
+        if (sinks_segment (&sinks, obuf[(slot)][0] + (size_t) q_ * out_bytes)) { aborted = 1; exit_status = 1; } \
+      if (per_segment && (kurto_fp || histo_fp)) {                                            /* :1378-1393, :1444-1450 */ \
+        if (vf_get_stats (h, 0, NULL, st_kur, NULL, NULL, st_kur_fb, NULL, st_w, st_histo) == VF_OK) { \
+          if (histo_fp) fwrite (st_histo, sizeof (uint32_t), 512, histo_fp); \
+          if (kurto_fp) { \
+            fwrite (st_kur, sizeof (float), 2 * (size_t) T * 25, kurto_fp); \
+            fwrite (st_kur_fb, sizeof (float), 2 * (size_t) T, block_kurto_fp); \
+            fwrite (st_w, sizeof (float), (size_t) T, weight_fp); \
+          } \
+        } \
+      } \
+      write_s += now_s () - tf0_; \
+    } while (0)
 
     for (;;) {                                                    /* seconds */
       uint64_t nbytes = 0;
@@ -414,35 +482,62 @@ int main (int argc, char **argv)
           if (ring_out) vf_ring_header_write (ring_out, dh);                   /* :981-984 */
           if (ring_co) vf_ring_header_write (ring_co, dh);                     /* :986-989 */
         }
+        if (cfg.keep_stats || cfg.do_histo) {
+          /* the reference's dump files: the .fil name with another extension (:861-870) */
+          char base[512], name[540];
+          snprintf (base, sizeof (base), "%s", fbfile);
+          char *dot = strrchr (base, '.');
+          if (dot) *dot = 0;
+          if (cfg.do_histo) { snprintf (name, sizeof (name), "%s.histo", base); histo_fp = fopen (name, "wb"); logmsg ("INFO", "Writing histograms to %s.\n", name); }
+          if (cfg.keep_stats && cfg.rfi_mode) {
+            snprintf (name, sizeof (name), "%s.kurto", base); kurto_fp = fopen (name, "wb"); logmsg ("INFO", "Writing kurtosis to %s.\n", name);
+            snprintf (name, sizeof (name), "%s.block_kurto", base); block_kurto_fp = fopen (name, "wb"); logmsg ("INFO", "Writing block kurtosis to %s.\n", name);
+            snprintf (name, sizeof (name), "%s.weights", base); weight_fp = fopen (name, "wb"); logmsg ("INFO", "Writing weights to %s.\n", name);
+            if (!kurto_fp || !block_kurto_fp || !weight_fp) { logmsg ("ERR", "cannot open the statistics files\n"); exit_status = 1; aborted = 1; blocks_open++; break; }
+          }
+        }
         logmsg ("INFO", "Starting sec=%d, thread=%d\n", vf_vdif_frame_second (vh), vf_vdif_thread_id (vh));
         first = 0;
       }
       const int current_sec = vf_vdif_frame_second (vh);
-      const int inject_now = cfg.inject_frb && (current_sec % 60 == 0);          /* :1098-1101 */
-      if (inject_now) logmsg ("INFO", "Injecting an FRB!!!\n");
 
-      for (int iseg = 0; iseg < SEG_PER_SEC && !aborted; ++iseg, ++seg_counter) {  /* :1108 */
-        const int slot = (int) (seg_counter & 1);
+      if (!per_segment) {
+        /* ---- the whole second at once.  Frames may sit anywhere in the block: the depacketiser places them
+         * by thread id and frame number across the second and skips frames of another second (:1015-1035) */
+        const int slot = (int) (seconds_done & 1);
         if (pend_slot[slot]) {
-          rc = vf_wait (h, slot);
-          pend_slot[slot] = 0;
-          if (rc) { logmsg ("ERR", "segment failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; break; }
-          if (fb_main) fwrite (obuf[slot][0], 1, out_bytes, fb_main);              /* :1438-1441 */
-          if (fb_raw) fwrite (obuf[slot][1], 1, out_bytes, fb_raw);
-          if (sinks_segment (&sinks, obuf[slot][0])) { aborted = 1; exit_status = 1; break; }
+          FINISH_SLOT (slot);
+          if (aborted) { blocks_open++; break; }
+          vf_ring_block_read_close (ring); blocks_open--;         /* the block of two seconds ago: its copy is done */
         }
-        if (cfg.inject_frb)
-          vf_set_frb_injection (h, inject_now ? iseg * 1024 : -1, 80.f, (float) (2e-3 * 10 * 1024), 1.05f);   /* :1238-1240 */
-        rc = vf_submit_vdif_async (h, slot, 0, blk + (size_t) iseg * (FRAMES_PER_SEC_2POL / SEG_PER_SEC) * VF_VD_FRM,
-                                   FRAMES_PER_SEC_2POL / SEG_PER_SEC, (uint32_t) (iseg * (VF_FRAME_RATE / SEG_PER_SEC)),
-                                   obuf[slot][0], obuf[slot][1]);
-        if (rc) { logmsg ("ERR", "submit failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; break; }
-        pend_slot[slot] = 1;
+        rc = vf_submit_vdif_block_async (h, slot, 0, blk, FRAMES_PER_SEC_2POL, 0, (long) current_sec, SEG_PER_SEC,
+                                         obuf[slot][0], obuf[slot][1]);
+        if (rc) { logmsg ("ERR", "submit failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; blocks_open++; break; }
+        pend_slot[slot] = 1; pend_sec[slot] = seconds_done;
+        seg_counter += SEG_PER_SEC;
+        blocks_open++;
+      } else {
+        /* ---- segment by segment (statistics dumps / histogram / FRB injection) */
+        const int inject_now = cfg.inject_frb && (current_sec % 60 == 0);        /* :1098-1101 */
+        if (inject_now) logmsg ("INFO", "Injecting an FRB!!!\n");
+        for (int iseg = 0; iseg < SEG_PER_SEC && !aborted; ++iseg, ++seg_counter) {  /* :1108 */
+          const int slot = (int) (seg_counter & 1);
+          if (pend_slot[slot]) { FINISH_SLOT (slot); if (aborted) break; }
+          if (cfg.inject_frb)
+            vf_set_frb_injection (h, inject_now ? iseg * 1024 : -1, 80.f, (float) (2e-3 * 10 * 1024), 1.05f);   /* :1238-1240 */
+          /* the window of this segment within the block; a frame the writer put elsewhere in the second is reported */
+          rc = vf_submit_vdif_block_async (h, slot, 0, blk + (size_t) iseg * (FRAMES_PER_SEC_2POL / SEG_PER_SEC) * VF_VD_FRM,
+                                           FRAMES_PER_SEC_2POL / SEG_PER_SEC, (uint32_t) (iseg * (VF_FRAME_RATE / SEG_PER_SEC)),
+                                           (long) current_sec, 1, obuf[slot][0], obuf[slot][1]);
+          if (rc) { logmsg ("ERR", "submit failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; break; }
+          pend_slot[slot] = 1; pend_sec[slot] = seconds_done;
+          if (kurto_fp || histo_fp) { FINISH_SLOT (slot); if (aborted) break; }   /* the dumps read the statistics of this segment */
+        }
+        /* two segments of this block may still be in flight: it stays open, and the block before it
+         * (whose segments have all been waited for by now) goes back to the writer */
+        if (blocks_open == 1) { vf_ring_block_read_close (ring); blocks_open = 0; }
+        blocks_open++;
       }
-      /* two segments of this block are still in flight: it stays open, and the block before it
-       * (whose segments have all been waited for by now) goes back to the writer */
-      if (blocks_open == 1) { vf_ring_block_read_close (ring); blocks_open = 0; }
-      blocks_open++;
       if (aborted) break;
       seconds_done++;
       if (seconds_done % 10 == 0) {                               /* RT_PROFILE watchdog, :1461-1477 */
@@ -456,16 +551,26 @@ int main (int argc, char **argv)
       }
       if (g_quit) break;
     }
-    /* end of the observation: drain the segments in flight, release the blocks */
+    /* end of the observation: drain what is in flight (oldest first), release the blocks */
     for (int k = 0; k < 2; ++k) {
-      const int slot = (int) ((seg_counter + k) & 1);
+      const int slot = per_segment ? (int) ((seg_counter + k) & 1) : (int) ((seconds_done + k) & 1);
       if (!pend_slot[slot]) continue;
-      rc = vf_wait (h, slot);
-      pend_slot[slot] = 0;
-      if (rc) { logmsg ("ERR", "segment failed: %s\n", vf_last_error (h)); exit_status = 1; continue; }
-      if (fb_main) fwrite (obuf[slot][0], 1, out_bytes, fb_main);
-      if (fb_raw) fwrite (obuf[slot][1], 1, out_bytes, fb_raw);
-      if (!aborted && sinks_segment (&sinks, obuf[slot][0])) { aborted = 1; exit_status = 1; }
+      do { FINISH_SLOT (slot); } while (0);
+    }
+#undef FINISH_SLOT
+    if (kurto_fp) fclose (kurto_fp);
+    if (block_kurto_fp) fclose (block_kurto_fp);
+    if (weight_fp) fclose (weight_fp);
+    if (histo_fp) fclose (histo_fp);
+    if (skipped_frames || missing_frames)
+      logmsg ("WARN", "observation: %ld frame(s) skipped, %ld frame(s) absent (their samples are zeros)\n", skipped_frames, missing_frames);
+    if (profile) {
+      /* the reference's per-stage table (:1538-1558) for the stages that still exist: the chain is two kernels */
+      logmsg ("INFO", "Device time.%.3f\n", dev_ms * 1e-3);
+      logmsg ("INFO", "Channelise..%.3f   (unpack, statistics, excision, FFT, detection: Convert + Kurtosis + FFT of the reference)\n", k1_ms * 1e-3);
+      logmsg ("INFO", "Normalise...%.3f   (Normalize + Pscrunch + Tscrunch + Digitize of the reference; includes the wait for bandpass order)\n", k2_ms * 1e-3);
+      logmsg ("INFO", "Wait........%.3f   (host blocked on the device or the copies)\n", wait_s);
+      logmsg ("INFO", "Write.......%.3f\n", write_s);
     }
     if (!first) {                                                 /* dada_hdu_unlock_write, :1498-1511 */
       if (ring_out) vf_ring_end_of_data (ring_out);
