@@ -346,7 +346,9 @@ def test_dada_db_and_genbase_into_ring(H, pkg, tmp_path):
 def test_psrdada_backed_ring_type_checks():
     """the ring surface of process_baseband on psrdada's own calls (host/psrdada/vf_ring_psrdada.c)
     compiles against headers carrying psrdada's prototypes (compile-only: psrdada is not in the image)"""
+    import os
     import subprocess
+    from conftest import ROOT
     r = subprocess.run(["make", "-C", os.path.join(ROOT, "vlite-fast_b200", "host"), "psrdada-check", "HOSTCC=/usr/bin/gcc"],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
