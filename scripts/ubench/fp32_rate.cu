@@ -67,6 +67,38 @@ __global__ void k (float *out, long long *cyc, float bx, float cx)
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// Dependent-issue latency: ONE warp, one accumulator, every instruction waits for the one before.
+template <int MODE>
+__global__ void klat (float *out, long long *cyc, float bx, float cx)
+{
+  float2 a = make_float2 (threadIdx.x * 0.001f, 0.5f);
+  const float2 b = make_float2 (bx, bx * 1.0001f), c = make_float2 (cx, cx * 0.999f);
+  long long t0 = clock64 ();
+#pragma unroll 1
+  for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      if (MODE == 0) a = fma2 (a, b, c);
+      if (MODE == 1) a = add2 (a, b);
+      if (MODE == 2) a = mul2 (a, b);
+      if (MODE == 3) { a.x = sfma (a.x, b.x, c.x); a.y = sfma (a.y, b.y, c.y); }      // two independent scalar chains
+      if (MODE == 4) a.x = sfma (a.x, b.x, c.x);                                       // one scalar chain
+    }
+  }
+  long long t1 = clock64 ();
+  out[threadIdx.x] = a.x + a.y;
+  if (threadIdx.x == 0) cyc[0] = t1 - t0;
+}
+
+template <int MODE> void runlat (const char *name, float *out, long long *cyc)
+{
+  klat<MODE><<<1, 32>>> (out, cyc, 1.0001f, 0.5f);
+  klat<MODE><<<1, 32>>> (out, cyc, 1.0001f, 0.5f);
+  cudaDeviceSynchronize ();
+  long long h; cudaMemcpy (&h, cyc, sizeof (long long), cudaMemcpyDeviceToHost);
+  printf ("%-44s %.2f cycles per dependent step\n", name, (double) h / (ITER * 32.0));
+}
+
 template <int MODE> void run (const char *name, int nsm, float *out, long long *cyc)
 {
   for (int threads = 128; threads <= 1024; threads *= 2) {
@@ -96,5 +128,11 @@ int main ()
   run<5> ("FFMA2 r,imm,r", nsm, out, cyc);
   run<6> ("FFMA r,imm,r (scalar)", nsm, out, cyc);
   run<7> ("FADD2 r, swap/neg r", nsm, out, cyc);
+  printf ("dependent chains, one warp:\n");
+  runlat<0> ("FFMA2 chain", out, cyc);
+  runlat<1> ("FADD2 chain", out, cyc);
+  runlat<2> ("FMUL2 chain", out, cyc);
+  runlat<3> ("2 x scalar FFMA chains (x and y of a float2)", out, cyc);
+  runlat<4> ("scalar FFMA chain", out, cyc);
   return 0;
 }

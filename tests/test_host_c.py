@@ -353,3 +353,14 @@ def test_psrdada_backed_ring_type_checks():
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "warning" not in r.stdout
+
+
+def test_float_thresholds_equal_the_double_compares():
+    """the 2-bit digitiser compares a float with double thresholds (src/pb_kernels.cu:660-663); the kernel uses the
+    smallest float >= each threshold, which gives the same answer for every float"""
+    for d, bits in ((-0.6109, 0xbf1c63f1), (0.3970, 0x3ecb4396), (1.4050, 0x3fb3d70b)):
+        f = np.array([bits], np.uint32).view(np.float32)[0]
+        assert float(f) >= d and float(np.nextafter(f, np.float32(-np.inf))) < d
+        xs = np.nextafter(f, np.float32(-np.inf)), f, np.nextafter(f, np.float32(np.inf))
+        for x in xs:
+            assert (float(x) < d) == (x < f)

@@ -108,6 +108,7 @@ struct vf_handle {
   float *coadd_sum;           /* [ave_nseg] summed tiles, then [ave_nseg][T/8] contributing-antenna counts: one reduce */
   uint8_t *coadd_out;
   int debug_sync, serial;
+  long long *k2_trace;        /* testing builds: vf_debug_k2_trace */
   char err[512];
 };
 
@@ -554,6 +555,16 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int ant0, int n_ant, co
   /* bp_scale = float(tsamp/tsmooth), src/process_baseband.cu:737-741 */
   k2.bp_scale = (float) (((double) VF_NFFT / 128000000 * VF_NSCRUNCH) / 1.0);
   k2.min_weight = c.min_weight;
+#ifdef VF_TESTING
+  k2.trace = h->k2_trace;
+#endif
+  {
+    /* the reference compares the float weight with the double MIN_WEIGHT (:537-538, :616-617); for a float w that
+     * is w >= (smallest float >= MIN_WEIGHT) */
+    float f = (float) c.min_weight;
+    if ((double) f < c.min_weight) f = nextafterf (f, INFINITY);
+    k2.min_weight_f = f;
+  }
   k2.out_main = d_main; k2.out_raw = d_raw; k2.out_stride = h->out_bytes;
   {
     /* tile slots of these segments in the ring of kept tiles (sized for the handle's n_antennas) */
@@ -859,6 +870,18 @@ int vf_process_device (vf_handle *h, int n_ant, int n_seg, const uint8_t *d_in,
 }
 
 #ifdef VF_TESTING
+/* TESTING BUILDS ONLY: clock64 stamps of the normaliser's chunk pipeline (first CTA): the next launches write
+ * [2 streams][4096 chunks][6 stamps] into a device buffer; copy it out with out != NULL */
+int vf_debug_k2_trace (vf_handle *h, long long *out)
+{
+  if (!h) return VF_ERR_ARG;
+  CK (cudaSetDevice (h->cfg.gpu_id));
+  const size_t n = 2 * 4096 * 6 * sizeof (long long);
+  if (!h->k2_trace) { CK (cudaMalloc ((void **) &h->k2_trace, n)); CK (cudaMemset (h->k2_trace, 0, n)); }
+  if (out) { int rc = vf_sync (h); if (rc) return rc; CK (cudaMemcpy (out, h->k2_trace, n, cudaMemcpyDeviceToHost)); }
+  return VF_OK;
+}
+
 /* TESTING BUILDS ONLY (libvlitefast_testing.so, csrc/vf_testing.h): self-check of the packed division used by the
  * normaliser: q_packed from the kernel's own routine, q_ref from CUDA's div.rn.f32, for n (even) host operand pairs */
 int vf_debug_division (vf_handle *h, const float *p, const float *b, float *q_packed, float *q_ref, size_t n)

@@ -68,6 +68,8 @@ struct vf_k2_params {
                                  stream was kept, 0 = zeroed by tscrunch_weights (:622-623); the co-add's count */
   size_t rowok_seg_elems;
   double min_weight;          /* MIN_WEIGHT, src/process_baseband.h:45 */
+  long long *trace;           /* TESTING BUILDS: clock64 stamps of the first CTA, [stream][chunk][6], else NULL */
+  float min_weight_f;         /* smallest float >= min_weight: for a float w, (double) w >= min_weight <=> w >= min_weight_f */
 };
 
 struct vf_depack_params {

@@ -444,6 +444,14 @@ int main (int argc, char **argv)
 
     for (;;) {                                                    /* seconds */
       uint64_t nbytes = 0;
+      if (!per_segment && pend_slot[seconds_done & 1]) {
+        /* the block of two seconds ago: finish it and hand its ring block back BEFORE asking for the next one
+         * (a ring of two blocks would otherwise have none left for the writer) */
+        const int slot_ = (int) (seconds_done & 1);
+        FINISH_SLOT (slot_);
+        vf_ring_block_read_close (ring); blocks_open--;
+        if (aborted) break;
+      }
       const unsigned char *blk = (const unsigned char *) vf_ring_block_read_open (ring, &nbytes);
       if (!blk) break;                                            /* end of data: primary exit, :1044-1051 */
       if (nbytes < SEC_BYTES) {
@@ -505,11 +513,6 @@ int main (int argc, char **argv)
         /* ---- the whole second at once.  Frames may sit anywhere in the block: the depacketiser places them
          * by thread id and frame number across the second and skips frames of another second (:1015-1035) */
         const int slot = (int) (seconds_done & 1);
-        if (pend_slot[slot]) {
-          FINISH_SLOT (slot);
-          if (aborted) { blocks_open++; break; }
-          vf_ring_block_read_close (ring); blocks_open--;         /* the block of two seconds ago: its copy is done */
-        }
         rc = vf_submit_vdif_block_async (h, slot, 0, blk, FRAMES_PER_SEC_2POL, 0, (long) current_sec, SEG_PER_SEC,
                                          obuf[slot][0], obuf[slot][1]);
         if (rc) { logmsg ("ERR", "submit failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; blocks_open++; break; }
