@@ -69,6 +69,7 @@ struct vf_k2_params {
   size_t rowok_seg_elems;
   double min_weight;          /* MIN_WEIGHT, src/process_baseband.h:45 */
   long long *trace;           /* TESTING BUILDS: clock64 stamps of the first CTA, [stream][chunk][6], else NULL */
+  float clip_floor;           /* set by vf_launch_k2: lower bound of 11 bp over a chunk / bp at its start (clip pre-test) */
   float min_weight_f;         /* smallest float >= min_weight: for a float w, (double) w >= min_weight <=> w >= min_weight_f */
 };
 
