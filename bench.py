@@ -10,7 +10,7 @@ count, NCCL reduce over the ranks when N > 1, scale and digitise on the root).
 
   value     device-resident: inputs already in HBM; CUDA events on the library's streams (vf_timer_begin/end,
             every stream of the handle including the co-add) around the K timed steps, max over ranks.
-  e2e       same metric through the host-buffer C ABI (vf_submit_async / vf_wait, pinned host memory allocated
+  e2e       same metric through the host-buffer C ABI (vf_submit_block_async / vf_wait, pinned host memory allocated
             on the GPU's NUMA node, double-buffered H2D and D2H inside the timed region, co-add included), wall
             clock between barriers, max over ranks.
   roofline  dominant kernel (the channeliser): algorithmic bytes per launch / its mean launch duration (CUDA
@@ -367,23 +367,33 @@ def main():
     # ---- end to end through host buffers ----------------------------------------
     e2e = None
     if not args.no_e2e:
+        nblk = [0]
+
         def second_e2e():
-            for s in range(SEG_PER_SEC):
-                slot = s & 1
-                if s >= 2:
-                    p.wait(slot)
-                p.submit_async(slot, [hn[s, a, 0] for a in range(n_ant)], [hn[s, a, 1] for a in range(n_ant)],
-                               [h_main[s, a].numpy() for a in range(n_ant)],
-                               [h_raw[s, a].numpy() for a in range(n_ant)] if h_raw is not None else None)
-            p.wait(0); p.wait(1)
+            """one antenna-second per antenna from pinned host memory: vf_submit_block_async takes the whole second
+            of all the rank's antennas in one copy and one launch pair; two seconds in flight (slots)"""
+            slot = nblk[0] & 1
+            if nblk[0] >= 2:
+                p.wait(slot)
+                # the co-add of the second that has just completed on this slot ... is issued right after its submit
+            p.submit_block_async(slot, n_ant, SEG_PER_SEC, hn, h_main.numpy(), h_raw.numpy() if h_raw is not None else None)
             p.coadd_batch_into(0, total_ant, SEG_PER_SEC, h_coadd.numpy() if rank == 0 else None, wait=False)
-        for _ in range(max(1, args.warmup * S // 8)):
+            nblk[0] += 1
+
+        def drain_e2e():
+            for sl in (0, 1):
+                if nblk[0] > sl:
+                    p.wait((nblk[0] - 1 - sl) & 1)
+            nblk[0] = 0
+        for _ in range(max(2, args.warmup * S // 8)):
             second_e2e()
+        drain_e2e()
         p.sync()
         barrier()
         t0 = time.perf_counter()
         for _ in range(K * S):
             second_e2e()
+        drain_e2e()
         p.sync()
         barrier()
         e_t = time.perf_counter() - t0
@@ -394,7 +404,7 @@ def main():
         e2e = {"value": ant_seconds / e_t, "unit": UNIT,
                "h2d_bytes_per_step": int(S * n_ant * 2 * NSAMP * SEG_PER_SEC),
                "d2h_bytes_per_step": int(S * (n_ant * out_bytes * nstream + (coadd_bytes if rank == 0 else 0)) * SEG_PER_SEC),
-               "api": "vf_submit_async/vf_wait + vf_coadd_batch, pinned host buffers, 2 slots",
+               "api": "vf_submit_block_async (one antenna-second of every antenna of the rank per call) / vf_wait + vf_coadd_batch, pinned host buffers, 2 slots",
                "h2d_gb_per_s_per_gpu": S * K * n_ant * 2 * NSAMP * SEG_PER_SEC / e_t / 1e9,
                "numa_cpulist": cpulist}
 

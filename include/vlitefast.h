@@ -125,6 +125,11 @@ int vf_process_vdif (vf_handle *h, int antenna, const void *frames, size_t nfram
 int vf_submit_async (vf_handle *h, int slot, int n_ant,
                      const uint8_t *const *pol0, const uint8_t *const *pol1, size_t nsamp_per_pol,
                      uint8_t *const *fb_main, uint8_t *const *fb_raw);
+/* A block of n_seg consecutive segments of n_ant antennas from ONE host buffer laid out
+ * [n_seg][n_ant][2][ffts_per_seg*12500] (one antenna: the ten 100-ms segments of a second back to back, pol 0 then
+ * pol 1 in each): one copy in, one launch pair over the block, outputs to fb_main / fb_raw [n_seg][n_ant][out_bytes].
+ * n_seg <= max_batch_segments.  Replaces n_seg rounds of src/process_baseband.cu:1108-1375. */
+int vf_submit_block_async (vf_handle *h, int slot, int n_ant, int n_seg, const uint8_t *in, uint8_t *fb_main, uint8_t *fb_raw);
 int vf_wait (vf_handle *h, int slot);
 /* Asynchronous form of vf_process_vdif: the frames are DMA'd straight from the
  * caller's (pinned) memory -- e.g. a block of the input ring -- and must stay
@@ -143,6 +148,10 @@ int vf_submit_vdif_async (vf_handle *h, int slot, int antenna, const void *frame
 int vf_submit_vdif_block_async (vf_handle *h, int slot, int antenna, const void *frames, size_t nframes,
                                 uint32_t first_frame, long expect_second, int n_seg, uint8_t *fb_main, uint8_t *fb_raw);
 int vf_vdif_report (vf_handle *h, int slot, unsigned int counts[5]);
+/* Allocates, for both slots, everything vf_submit_vdif_block_async (n_seg) would otherwise allocate on its first call:
+ * start-up work, as the reference's allocations are (src/process_baseband.cu:572-690), so that the first second of an
+ * observation costs what the others do.  Optional. */
+int vf_reserve_vdif_blocks (vf_handle *h, int n_seg);
 
 /* Device-resident form: d_in is [n_ant][2][ffts_per_seg*12500] bytes on the
  * device (256-byte aligned), d_fb_main / d_fb_raw [n_ant][out_bytes].  Enqueued
@@ -154,6 +163,10 @@ int vf_sync (vf_handle *h);
 /* elapsed device time between the start and end of the last vf_process_device
  * / vf_process_* call, from CUDA events on the library's stream (ms) */
 int vf_last_elapsed_ms (vf_handle *h, float *total_ms, float *k1_ms, float *k2_ms);
+/* the same for the last asynchronous submission on `slot` (vf_submit_*_async), after its vf_wait: total from the
+ * start of the copy in to the end of the copy out; the per-stage accumulators of the reference's RT_PROFILE table
+ * (src/process_baseband.cu:1538-1563) */
+int vf_slot_elapsed_ms (vf_handle *h, int slot, float *total_ms, float *k1_ms, float *k2_ms);
 /* Device-side stopwatch (CUDA events) over everything enqueued on the handle's streams -- segments and co-adds --
  * between the two calls; vf_timer_end waits for that work and returns the elapsed milliseconds. */
 int vf_timer_begin (vf_handle *h);

@@ -18,6 +18,8 @@ timeout 300 python bench.py --steps 5 --warmup 3 --nbit 8 --no-cpu-baseline --no
 timeout 300 vlite-fast_b200/bin/process_baseband -S 2 -L 5 -F -w 0 -j > /dev/null 2>&1
 timeout 300 vlite-fast_b200/bin/process_baseband -S 10 -L 6 -F -w 0 -j -T -o > $O/exe_60s.log 2>$O/exe_60s.err
 python scripts/ubench/h2d_rate.py > $O/h2d_rate.log 2>&1
+timeout 120 python scripts/k2_time.py > $O/kernel_times_serialised.log 2>&1
+timeout 120 python scripts/k2_trace.py > $O/k2_trace.log 2>&1
 # launch list (serialised, cold-cache per-launch times: shares only), then one full capture of each kernel
 CMD="python bench.py --steps 1 --warmup 3 --seconds-per-step 4 --no-cpu-baseline --no-legacy --no-e2e --no-check"
 $CMD > $O/plain.log 2>&1 &&

@@ -20,6 +20,9 @@ def test_libvlitefast_exports_header(pkg):
     assert len(names) >= 25
     for n in names:
         assert hasattr(L, n), "libvlitefast.so lacks %s" % n
+    # every entry point has its prototype declared to ctypes: an undeclared one would pass pointers as 32-bit ints
+    unbound = [n for n in names if getattr(L, n).argtypes is None]
+    assert not unbound, "binding.py declares no argtypes for %s" % unbound
 
 
 def test_hostlib_exports_headers(pkg):

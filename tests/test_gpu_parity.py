@@ -154,8 +154,44 @@ def test_async_double_buffer_equals_sync(pkg):
         p.wait(0); p.wait(1)
         with pytest.raises(pkg.VfError):
             p.wait(0)
+        # per-stage device times of an asynchronous submission (the executable's RT_PROFILE table)
+        for slot in (0, 1):
+            total, k1, k2 = p.slot_elapsed_ms(slot)
+            assert 0 < k1 < total and 0 < k2 < total and k1 + k2 <= total * 1.001, (total, k1, k2)
     for s in range(nseg):
         assert np.array_equal(outs[s], want[s]), s
+
+
+def test_host_block_equals_per_segment(pkg):
+    """vf_submit_block_async (a block of segments x antennas from one host buffer, one launch pair) gives the bytes of
+    per-segment vf_process_batch calls, on both slots, with the bandpass carried from block to block"""
+    T, nseg, nant, nblk = 16, 3, 2, 3
+    rng_in = np.empty((nblk, nseg, nant, 2, T * 12500), np.uint8)
+    for b in range(nblk):
+        for s in range(nseg):
+            for a in range(nant):
+                p0, p1 = make_input(pkg, T, seed=61, antenna=a, sample0=(b * nseg + s) * T * 12500, **RFI)
+                rng_in[b, s, a, 0], rng_in[b, s, a, 1] = p0, p1
+    with pkg.Pipeline(ffts_per_seg=T, nbit=2, rfi_mode=2, n_antennas=nant) as p:
+        want = [p.process_batch([rng_in[b, s, a, 0] for a in range(nant)], [rng_in[b, s, a, 1] for a in range(nant)])
+                for b in range(nblk) for s in range(nseg)]
+    with pkg.Pipeline(ffts_per_seg=T, nbit=2, rfi_mode=2, n_antennas=nant, max_batch_segments=nseg) as p:
+        mains = np.zeros((nblk, nseg, nant, p.out_bytes), np.uint8)
+        raws = np.zeros_like(mains)
+        for b in range(nblk):
+            if b >= 2:
+                p.wait(b & 1)
+            p.submit_block_async(b & 1, nant, nseg, rng_in[b], mains[b], raws[b])
+        p.wait(1); p.wait(0)
+        with pytest.raises(pkg.VfError):
+            p.submit_block_async(0, nant, nseg + 1, np.zeros((nseg + 1, nant, 2, T * 12500), np.uint8),
+                                 np.zeros((nseg + 1, nant, p.out_bytes), np.uint8), None)
+    for b in range(nblk):
+        for s in range(nseg):
+            wm, wr = want[b * nseg + s]
+            for a in range(nant):
+                assert np.array_equal(mains[b, s, a], wm[a]), (b, s, a)
+                assert np.array_equal(raws[b, s, a], wr[a]), (b, s, a)
 
 
 def test_device_resident_equals_host(pkg):

@@ -68,6 +68,8 @@ def lib(testing=False):
     L.vf_submit_vdif_async.argtypes = [vp, i, i, vp, sz, C.c_uint32, u8p, u8p]
     L.vf_submit_vdif_block_async.argtypes = [vp, i, i, vp, sz, C.c_uint32, C.c_long, i, u8p, u8p]
     L.vf_vdif_report.argtypes = [vp, i, C.POINTER(C.c_uint * 5)]
+    L.vf_reserve_vdif_blocks.argtypes = [vp, i]
+    L.vf_submit_block_async.argtypes = [vp, i, i, i, vp, vp, vp]
     L.vf_process_device.argtypes = [vp, i, i, vp, vp, vp]
     L.vf_sync.argtypes = [vp]
     L.vf_set_serial.argtypes = [vp, i]
@@ -77,8 +79,11 @@ def lib(testing=False):
         L.vf_debug_division.argtypes = [vp, vp, vp, vp, vp, sz]
     fp = C.POINTER(C.c_float)
     L.vf_last_elapsed_ms.argtypes = [vp, fp, fp, fp]
+    L.vf_slot_elapsed_ms.argtypes = [vp, i, fp, fp, fp]
     L.vf_bind_thread_to_gpu.argtypes = [i, C.c_char_p, sz]
     L.vf_host_alloc.argtypes = [C.POINTER(vp), sz]
+    L.vf_host_register.argtypes = [vp, sz]
+    L.vf_host_unregister.argtypes = [vp]
     L.vf_host_free.argtypes = [vp]
     L.vf_get_stats.argtypes = [vp, i] + [vp] * 8
     L.vf_get_mask.argtypes = [vp, i, vp]
@@ -241,6 +246,11 @@ class Pipeline:
         self._ck(self.L.vf_submit_async(self.h, slot, n, self._arrays(pol0s), self._arrays(pol1s), self.nsamp,
                                         self._arrays(mains), self._arrays(raws) if raws else None))
 
+    def submit_block_async(self, slot, n_ant, n_seg, block, mains, raws=None):
+        """vf_submit_block_async: block is one host array [n_seg][n_ant][2][nsamp]; outputs [n_seg][n_ant][out_bytes]"""
+        assert block.size == n_seg * n_ant * 2 * self.nsamp and mains.size == n_seg * n_ant * self.out_bytes
+        self._ck(self.L.vf_submit_block_async(self.h, slot, n_ant, n_seg, _ptr(block), _ptr(mains), _ptr(raws)))
+
     def wait(self, slot):
         self._ck(self.L.vf_wait(self.h, slot))
 
@@ -293,6 +303,12 @@ class Pipeline:
     def last_elapsed_ms(self):
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         self._ck(self.L.vf_last_elapsed_ms(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def slot_elapsed_ms(self, slot):
+        """(total, K1, K2) device ms of the last asynchronous submission on `slot`, after wait(slot)"""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        self._ck(self.L.vf_slot_elapsed_ms(self.h, slot, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
     # ---- inspection ---------------------------------------------------------

@@ -41,6 +41,8 @@ struct vf_slot {
   uint32_t *mask;             /* [n_ant][T] */
   uint8_t *d_out_main, *d_out_raw;   /* [n_ant][out_bytes] */
   cudaEvent_t ev_k2, ev_done;
+  cudaEvent_t ev_t[5];        /* asynchronous submissions: start, before K1, after K1, after K2, end (vf_slot_elapsed_ms) */
+  int t_valid;
   int pending;                /* vf_submit_*_async issued, vf_wait not yet called */
   unsigned int *d_bad, *h_bad;/* VDIF input: [0] frames outside the window, [1] frames of another second, [2] frames placed, [3] invalid-bit frames */
   uint32_t first_frame;
@@ -212,6 +214,7 @@ static int vf_alloc_slot (vf_handle *h, vf_slot *s)
   if (mode == 2) CK (cudaMalloc ((void **) &s->d_out_raw, na * h->out_bytes));
   CK (cudaEventCreateWithFlags (&s->ev_k2, cudaEventDisableTiming));
   CK (cudaEventCreateWithFlags (&s->ev_done, cudaEventDisableTiming));
+  for (int i = 0; i < 5; ++i) CK (cudaEventCreate (&s->ev_t[i]));
   return VF_OK;
 }
 
@@ -257,6 +260,7 @@ int vf_destroy (vf_handle *h)
     cudaFree (s->pw); cudaFree (s->pw_fb); cudaFree (s->histo);
     if (s->ev_k2) cudaEventDestroy (s->ev_k2);
     if (s->ev_done) cudaEventDestroy (s->ev_done);
+    for (int i = 0; i < 5; ++i) if (s->ev_t[i]) cudaEventDestroy (s->ev_t[i]);
     if (s->st) cudaStreamDestroy (s->st);
   }
   cudaFree (h->bp_raw); cudaFree (h->bp_kur); cudaFree (h->tw); cudaFree (h->wtab);
@@ -485,7 +489,7 @@ int vf_host_unregister (void *p)
 /* ---- the launch sequence of one segment on one slot ---------------------- *
  * d_in: [n_ant][2][T*12500] on the device, antenna a of the launch being antenna ant0 + a of the handle
  * (bandpass state, statistics, kept tiles).  Outputs to d_main / d_raw ([n_ant][out_bytes]).
- * timed >= 0: record the K1/K2 events of that index. */
+ * timed >= 0: record the K1/K2 events of that index; timed == -2: the slot's own events (asynchronous submissions). */
 static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int ant0, int n_ant, const uint8_t *d_in,
                                uint8_t *d_main, uint8_t *d_raw, int timed, int n_seg = 1)
 {
@@ -530,9 +534,11 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int ant0, int n_ant, co
   }
   if (h->serial && h->have_k2_last) CK (cudaStreamWaitEvent (s->st, h->ev_k2_last, 0));
   if (timed >= 0) CK (cudaEventRecord (h->ev_ka[timed], s->st));
+  if (timed == -2) CK (cudaEventRecord (s->ev_t[1], s->st));
   CK (vf_launch_k1 (k1, grid, threads, s->st));
   if (h->debug_sync) CK (cudaStreamSynchronize (s->st));      /* VF_DEBUG_SYNC=1: attribute faults to a kernel */
   if (timed >= 0) CK (cudaEventRecord (h->ev_kb[timed], s->st));
+  if (timed == -2) CK (cudaEventRecord (s->ev_t[2], s->st));
 
   /* the bandpass makes K2 launches sequential in segment order */
   if (h->have_k2_last) CK (cudaStreamWaitEvent (s->st, h->ev_k2_last, 0));
@@ -585,6 +591,7 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int ant0, int n_ant, co
   CK (vf_launch_k2 (k2, s->st));
   if (h->debug_sync) CK (cudaStreamSynchronize (s->st));
   if (timed >= 0) CK (cudaEventRecord (h->ev_kc[timed], s->st));
+  if (timed == -2) CK (cudaEventRecord (s->ev_t[3], s->st));
   CK (cudaEventRecord (h->ev_k2_last, s->st));
   h->have_k2_last = 1;
   return VF_OK;
@@ -639,19 +646,58 @@ int vf_submit_async (vf_handle *h, int slot, int n_ant,
   vf_slot *s = &h->slot[slot];
   if (s->pending) return vf_fail (h, VF_ERR_STATE, "slot %d submitted twice without vf_wait", slot);
   CK (cudaSetDevice (h->cfg.gpu_id));
+  CK (cudaEventRecord (s->ev_t[0], s->st));
   for (int a = 0; a < n_ant; ++a) {                       /* H2D, src/process_baseband.cu:1117-1122 */
     if (!pol0[a] || !pol1[a] || !fb_main[a]) return vf_fail (h, VF_ERR_ARG, "null buffer for antenna %d", a);
     CK (cudaMemcpyAsync (s->d_in + (size_t) a * 2 * h->nsamp, pol0[a], h->nsamp, cudaMemcpyHostToDevice, s->st));
     CK (cudaMemcpyAsync (s->d_in + ((size_t) a * 2 + 1) * h->nsamp, pol1[a], h->nsamp, cudaMemcpyHostToDevice, s->st));
   }
-  rc = vf_enqueue_segment (h, s, 0, n_ant, s->d_in, s->d_out_main, s->d_out_raw, -1);
+  rc = vf_enqueue_segment (h, s, 0, n_ant, s->d_in, s->d_out_main, s->d_out_raw, -2);
   if (rc) return rc;
   for (int a = 0; a < n_ant; ++a) {                       /* D2H, :1370-1375 */
     CK (cudaMemcpyAsync (fb_main[a], s->d_out_main + (size_t) a * h->out_bytes, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
     if (h->cfg.rfi_mode == 2 && fb_raw && fb_raw[a])
       CK (cudaMemcpyAsync (fb_raw[a], s->d_out_raw + (size_t) a * h->out_bytes, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
   }
+  CK (cudaEventRecord (s->ev_t[4], s->st));
   CK (cudaEventRecord (s->ev_done, s->st));
+  s->t_valid = 1;
+  s->pending = 1;
+  return VF_OK;
+}
+
+static int vf_slot_reserve_blk (vf_handle *h, vf_slot *s, int units);
+
+/* n_seg consecutive segments of n_ant antennas from ONE host buffer laid out as the device wants it,
+ * in [n_seg][n_ant][2][nsamp] (for one antenna: the ten 100-ms segments of a second back to back, each pol 0 then
+ * pol 1): one copy in, one launch pair over the block, one copy out per stream into fb_main / fb_raw
+ * [n_seg][n_ant][out_bytes].  The asynchronous form of vf_process_device for host buffers; vf_wait (slot) completes it.
+ * Replaces n_seg rounds of the reference's per-segment H2D / kernels / D2H (src/process_baseband.cu:1108-1375). */
+int vf_submit_block_async (vf_handle *h, int slot, int n_ant, int n_seg, const uint8_t *in, uint8_t *fb_main, uint8_t *fb_raw)
+{
+  if (!h || !in || !fb_main) return VF_ERR_ARG;
+  if (slot < 0 || slot > 1) return vf_fail (h, VF_ERR_ARG, "bad slot");
+  if (n_ant < 1 || n_ant > h->n_ant) return vf_fail (h, VF_ERR_ARG, "n_ant %d outside 1..%d", n_ant, h->n_ant);
+  if (n_seg < 1 || n_seg > vf_max_batch (h))
+    return vf_fail (h, VF_ERR_ARG, "n_seg %d outside 1..%d (max_batch_segments; 1 with keep_stats / do_histo / inject_frb)", n_seg, vf_max_batch (h));
+  vf_slot *s = &h->slot[slot];
+  if (s->pending) return vf_fail (h, VF_ERR_STATE, "slot %d submitted twice without vf_wait", slot);
+  CK (cudaSetDevice (h->cfg.gpu_id));
+  int rc = vf_ensure_batch (h, n_seg);
+  if (rc) return rc;
+  rc = vf_slot_reserve_blk (h, s, n_seg * n_ant);
+  if (rc) return rc;
+  const size_t units = (size_t) n_seg * n_ant;
+  CK (cudaEventRecord (s->ev_t[0], s->st));
+  CK (cudaMemcpyAsync (s->d_in_blk, in, units * 2 * h->nsamp, cudaMemcpyHostToDevice, s->st));       /* :1117-1122 */
+  rc = vf_enqueue_segment (h, s, 0, n_ant, s->d_in_blk, s->d_out_blk[0], s->d_out_blk[1], -2, n_seg);
+  if (rc) return rc;
+  CK (cudaMemcpyAsync (fb_main, s->d_out_blk[0], units * h->out_bytes, cudaMemcpyDeviceToHost, s->st));  /* :1370-1375 */
+  if (h->cfg.rfi_mode == 2 && fb_raw)
+    CK (cudaMemcpyAsync (fb_raw, s->d_out_blk[1], units * h->out_bytes, cudaMemcpyDeviceToHost, s->st));
+  CK (cudaEventRecord (s->ev_t[4], s->st));
+  CK (cudaEventRecord (s->ev_done, s->st));
+  s->t_valid = 1;
   s->pending = 1;
   return VF_OK;
 }
@@ -694,14 +740,17 @@ static int vf_submit_one_async (vf_handle *h, int slot, int antenna, const uint8
 {
   vf_slot *s = &h->slot[slot];
   CK (cudaSetDevice (h->cfg.gpu_id));
+  CK (cudaEventRecord (s->ev_t[0], s->st));
   CK (cudaMemcpyAsync (s->d_in, pol0, h->nsamp, cudaMemcpyHostToDevice, s->st));      /* H2D, src/process_baseband.cu:1117-1122 */
   CK (cudaMemcpyAsync (s->d_in + h->nsamp, pol1, h->nsamp, cudaMemcpyHostToDevice, s->st));
-  int rc = vf_enqueue_segment (h, s, antenna, 1, s->d_in, s->d_out_main, s->d_out_raw, -1);
+  int rc = vf_enqueue_segment (h, s, antenna, 1, s->d_in, s->d_out_main, s->d_out_raw, -2);
   if (rc) return rc;
   CK (cudaMemcpyAsync (fb_main, s->d_out_main, h->out_bytes, cudaMemcpyDeviceToHost, s->st));   /* D2H, :1370-1375 */
   if (h->cfg.rfi_mode == 2 && fb_raw)
     CK (cudaMemcpyAsync (fb_raw, s->d_out_raw, h->out_bytes, cudaMemcpyDeviceToHost, s->st));
+  CK (cudaEventRecord (s->ev_t[4], s->st));
   CK (cudaEventRecord (s->ev_done, s->st));
+  s->t_valid = 1;
   s->pending = 1;
   return VF_OK;
 }
@@ -728,6 +777,64 @@ int vf_process_segment (vf_handle *h, int antenna,
   return rc;
 }
 
+/* planar input and outputs of a block on slot s: units = segments x antennas */
+static int vf_slot_reserve_blk (vf_handle *h, vf_slot *s, int units)
+{
+  if (s->blk_cap >= units) return VF_OK;
+  cudaFree (s->d_in_blk); cudaFree (s->d_out_blk[0]); cudaFree (s->d_out_blk[1]);
+  s->d_in_blk = NULL; s->d_out_blk[0] = s->d_out_blk[1] = NULL; s->blk_cap = 0;
+  CK (cudaMalloc ((void **) &s->d_in_blk, (size_t) units * 2 * h->nsamp));
+  CK (cudaMalloc ((void **) &s->d_out_blk[0], (size_t) units * h->out_bytes));
+  if (h->cfg.rfi_mode == 2) CK (cudaMalloc ((void **) &s->d_out_blk[1], (size_t) units * h->out_bytes));
+  s->blk_cap = units;
+  return VF_OK;
+}
+
+/* device buffers of a VDIF submission of n_seg segments on slot s: the frames as they arrive, and for n_seg > 1 the
+ * planar input and the outputs of the block (a single segment uses the slot's own) */
+static int vf_slot_reserve_vdif (vf_handle *h, vf_slot *s, size_t bytes, int n_seg)
+{
+  const size_t per_pol = h->nsamp / VF_VD_DAT;
+  if (s->frames_cap < bytes) {
+    cudaFree (s->d_frames); s->d_frames = NULL; s->frames_cap = 0;
+    size_t cap = bytes > 2 * per_pol * n_seg * VF_VD_FRM ? bytes : 2 * per_pol * n_seg * VF_VD_FRM;
+    CK (cudaMalloc ((void **) &s->d_frames, cap));
+    s->frames_cap = cap;
+  }
+  if (!s->d_bad) {
+    CK (cudaMalloc ((void **) &s->d_bad, 4 * sizeof (unsigned int)));
+    CK (cudaMallocHost ((void **) &s->h_bad, 4 * sizeof (unsigned int)));
+  }
+  if (n_seg > 1) {
+    /* statistics dumps, histogram and FRB injection are per segment (vf_max_batch) */
+    if (vf_max_batch (h) < n_seg) return vf_fail (h, VF_ERR_STATE, "blocks of %d segments need a handle without keep_stats / do_histo / inject_frb", n_seg);
+    int rc = vf_ensure_batch (h, n_seg);
+    if (rc) return rc;
+    rc = vf_slot_reserve_blk (h, s, n_seg);
+    if (rc) return rc;
+  }
+  return VF_OK;
+}
+
+/* Everything vf_submit_vdif_block_async (n_seg) would otherwise allocate on its first call, for both slots, and the
+ * kernels' code on the device: called once at start-up (the reference allocates at start-up too,
+ * src/process_baseband.cu:572-690) so that the first second of an observation costs what the others do. */
+int vf_reserve_vdif_blocks (vf_handle *h, int n_seg)
+{
+  if (!h) return VF_ERR_ARG;
+  if (n_seg < 1 || n_seg > 16) return vf_fail (h, VF_ERR_ARG, "n_seg %d outside 1..16", n_seg);
+  if (h->nsamp % VF_VD_DAT) return vf_fail (h, VF_ERR_ARG, "the VDIF entry points need segments of whole frames (ffts_per_seg a multiple of 2)");
+  CK (cudaSetDevice (h->cfg.gpu_id));
+  const size_t bytes = 2 * (h->nsamp / VF_VD_DAT) * (size_t) n_seg * VF_VD_FRM;
+  for (int i = 0; i < 2; ++i) {
+    if (h->slot[i].pending) return vf_fail (h, VF_ERR_STATE, "slot %d has a submission in flight", i);
+    int rc = vf_slot_reserve_vdif (h, &h->slot[i], bytes, n_seg);
+    if (rc) return rc;
+  }
+  CK (cudaDeviceSynchronize ());
+  return VF_OK;
+}
+
 /* Frames of n_seg consecutive segments of one antenna (n_seg = 10: a one-second block of the input ring), in any
  * order: one copy, one depacketiser launch that places every frame by (thread id, frame number) across the whole
  * block -- as the reference's host loop does across the second, src/process_baseband.cu:1015-1035 -- and ONE
@@ -749,32 +856,11 @@ static int vf_submit_vdif_common (vf_handle *h, int slot, int antenna, const voi
   if (s->pending) return vf_fail (h, VF_ERR_STATE, "slot %d submitted twice without vf_wait", slot);
   CK (cudaSetDevice (h->cfg.gpu_id));
   const size_t bytes = nframes * VF_VD_FRM;
-  if (s->frames_cap < bytes) {
-    cudaFree (s->d_frames); s->d_frames = NULL; s->frames_cap = 0;
-    size_t cap = bytes > 2 * per_pol * n_seg * VF_VD_FRM ? bytes : 2 * per_pol * n_seg * VF_VD_FRM;
-    CK (cudaMalloc ((void **) &s->d_frames, cap));
-    s->frames_cap = cap;
-  }
-  if (!s->d_bad) {
-    CK (cudaMalloc ((void **) &s->d_bad, 4 * sizeof (unsigned int)));
-    CK (cudaMallocHost ((void **) &s->h_bad, 4 * sizeof (unsigned int)));
-  }
+  int rc0 = vf_slot_reserve_vdif (h, s, bytes, n_seg);
+  if (rc0) return rc0;
   uint8_t *d_in = s->d_in, *d_main = s->d_out_main, *d_raw = s->d_out_raw;
-  if (n_seg > 1) {
-    /* statistics dumps, histogram and FRB injection are per segment (vf_max_batch) */
-    if (vf_max_batch (h) < n_seg) return vf_fail (h, VF_ERR_STATE, "blocks of %d segments need a handle without keep_stats / do_histo / inject_frb", n_seg);
-    int rc = vf_ensure_batch (h, n_seg);
-    if (rc) return rc;
-    if (s->blk_cap < n_seg) {
-      cudaFree (s->d_in_blk); cudaFree (s->d_out_blk[0]); cudaFree (s->d_out_blk[1]);
-      s->d_in_blk = NULL; s->d_out_blk[0] = s->d_out_blk[1] = NULL; s->blk_cap = 0;
-      CK (cudaMalloc ((void **) &s->d_in_blk, (size_t) n_seg * 2 * h->nsamp));
-      CK (cudaMalloc ((void **) &s->d_out_blk[0], (size_t) n_seg * h->out_bytes));
-      if (h->cfg.rfi_mode == 2) CK (cudaMalloc ((void **) &s->d_out_blk[1], (size_t) n_seg * h->out_bytes));
-      s->blk_cap = n_seg;
-    }
-    d_in = s->d_in_blk; d_main = s->d_out_blk[0]; d_raw = s->d_out_blk[1];
-  }
+  if (n_seg > 1) { d_in = s->d_in_blk; d_main = s->d_out_blk[0]; d_raw = s->d_out_blk[1]; }
+  CK (cudaEventRecord (s->ev_t[0], s->st));
   CK (cudaMemcpyAsync (s->d_frames, frames, bytes, cudaMemcpyHostToDevice, s->st));
   CK (cudaMemsetAsync (d_in, 0, (size_t) n_seg * 2 * h->nsamp, s->st));
   CK (cudaMemsetAsync (s->d_bad, 0, 4 * sizeof (unsigned int), s->st));
@@ -784,12 +870,14 @@ static int vf_submit_vdif_common (vf_handle *h, int slot, int antenna, const voi
   dp.frame0 = first_frame; dp.nframes_per_pol = (long long) per_pol * n_seg; dp.expect_second = expect_second; dp.bad = s->d_bad;
   CK (vf_launch_depack (dp, s->st));
   CK (cudaMemcpyAsync (s->h_bad, s->d_bad, 4 * sizeof (unsigned int), cudaMemcpyDeviceToHost, s->st));
-  int rc = vf_enqueue_segment (h, s, antenna, 1, d_in, d_main, d_raw, -1, n_seg);
+  int rc = vf_enqueue_segment (h, s, antenna, 1, d_in, d_main, d_raw, -2, n_seg);
   if (rc) return rc;
   CK (cudaMemcpyAsync (fb_main, d_main, (size_t) n_seg * h->out_bytes, cudaMemcpyDeviceToHost, s->st));
   if (h->cfg.rfi_mode == 2 && fb_raw)
     CK (cudaMemcpyAsync (fb_raw, d_raw, (size_t) n_seg * h->out_bytes, cudaMemcpyDeviceToHost, s->st));
+  CK (cudaEventRecord (s->ev_t[4], s->st));
   CK (cudaEventRecord (s->ev_done, s->st));
+  s->t_valid = 1;
   s->pending = 2;               /* 2: vf_wait also reports frames that were skipped */
   s->first_frame = first_frame;
   s->blk_expected = 2 * per_pol * n_seg;
@@ -966,6 +1054,21 @@ int vf_last_elapsed_ms (vf_handle *h, float *total_ms, float *k1_ms, float *k2_m
    * any wait for the previous segment's K2 (bandpass order) */
   if (k1_ms) *k1_ms = a;
   if (k2_ms) *k2_ms = b;
+  return VF_OK;
+}
+
+/* device times of the last asynchronous submission on `slot` (after vf_wait): total from the start of its copy in to
+ * the end of its copy out, and the two kernels (K2 includes any wait for the bandpass order of the other slot) */
+int vf_slot_elapsed_ms (vf_handle *h, int slot, float *total_ms, float *k1_ms, float *k2_ms)
+{
+  if (!h || slot < 0 || slot > 1) return VF_ERR_ARG;
+  vf_slot *s = &h->slot[slot];
+  if (!s->t_valid) return vf_fail (h, VF_ERR_STATE, "nothing submitted on slot %d yet", slot);
+  if (s->pending) return vf_fail (h, VF_ERR_STATE, "slot %d not waited for", slot);
+  CK (cudaEventSynchronize (s->ev_t[4]));
+  if (total_ms) CK (cudaEventElapsedTime (total_ms, s->ev_t[0], s->ev_t[4]));
+  if (k1_ms) CK (cudaEventElapsedTime (k1_ms, s->ev_t[1], s->ev_t[2]));
+  if (k2_ms) CK (cudaEventElapsedTime (k2_ms, s->ev_t[2], s->ev_t[3]));
   return VF_OK;
 }
 

@@ -336,6 +336,10 @@ int main (int argc, char **argv)
    * one depacketiser launch over the second, one launch pair over its ten segments. */
   const int per_segment = cfg.keep_stats || cfg.do_histo || cfg.inject_frb;
   const int seg_per_submit = per_segment ? 1 : SEG_PER_SEC;
+  if (!per_segment && (rc = vf_reserve_vdif_blocks (h, SEG_PER_SEC))) {          /* start-up, like the reference's allocations (:572-690) */
+    logmsg ("ERR", "vf_reserve_vdif_blocks: %s (%s)\n", vf_strerror (rc), vf_last_error (h));
+    return 20;
+  }
   uint8_t *obuf[2][2] = {{NULL, NULL}, {NULL, NULL}};             /* [slot][main, raw] pinned */
   for (int s = 0; s < 2; ++s)
     for (int k = 0; k < 2; ++k)
@@ -423,7 +427,7 @@ int main (int argc, char **argv)
       } \
       if (rc) { logmsg ("ERR", "segment failed: %s\n", vf_last_error (h)); aborted = 1; exit_status = 1; break; } \
       { unsigned int cnt_[5]; if (vf_vdif_report (h, (slot), cnt_) == VF_OK && cnt_[2] < cnt_[4]) missing_frames += cnt_[4] - cnt_[2]; } \
-      if (profile) { float a_ = 0, b_ = 0, c_ = 0; if (vf_last_elapsed_ms (h, &a_, &b_, &c_) == VF_OK) { dev_ms += a_; k1_ms += b_; k2_ms += c_; } } \
+      if (profile) { float a_ = 0, b_ = 0, c_ = 0; if (vf_slot_elapsed_ms (h, (slot), &a_, &b_, &c_) == VF_OK) { dev_ms += a_; k1_ms += b_; k2_ms += c_; } } \
       const double tf0_ = now_s (); \
       if (fb_main) fwrite (obuf[(slot)][0], 1, (size_t) seg_per_submit * out_bytes, fb_main);     /* :1438-1441 */ \
       if (fb_raw) fwrite (obuf[(slot)][1], 1, (size_t) seg_per_submit * out_bytes, fb_raw); \
