@@ -37,6 +37,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
+# the co-add's reduce must fit into the SMs the normaliser leaves free (vf_coadd_init, vf_api.cu): NCCL reads this when the
+# process creates its first communicator, which is torch.distributed's below
+os.environ.setdefault("NCCL_MAX_NCHANNELS", "8")
+
 SEG_PER_SEC = 10
 T = 1024
 NSAMP = T * 12500

@@ -1285,6 +1285,13 @@ int vf_coadd_init (vf_handle *h, int nranks, int rank, const void *nccl_unique_i
   h->nranks = nranks; h->rank = rank;
   if (nranks > 1) {
     if (!nccl_unique_id) return vf_fail (h, VF_ERR_ARG, "nranks > 1 needs the NCCL unique id");
+    /* The reduce of a second (21 MB per rank) has a whole second of slack, but its CTAs need SMs of their own: both
+     * kernels of the chain fill their SMs' registers, and the normaliser is a single wave of 128 CTAs that leaves 20 SMs
+     * free.  NCCL's default channel count takes more than those (measured at 4 GPUs, round 2: 4110 antenna-seconds/s
+     * with the default, 4230 with 8 channels, 4298 = 4 x the 1-GPU rate), so a late normaliser CTA stretches its launch.
+     * NCCL reads the variable when the process creates its first communicator: a caller that already has one
+     * (torch.distributed) sets it itself before that (bench.py does). */
+    setenv ("NCCL_MAX_NCHANNELS", "8", 0);
     int rc = vf_nccl_load (h);
     if (rc) return rc;
     vf_nccl_id id;
