@@ -221,26 +221,36 @@ def test_device_resident_equals_host(pkg):
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_pipelined_channeliser_stress(pkg, mode):
     """the two warp groups of the pipelined channeliser hand buffers over through named barriers and mbarriers:
-    odd item counts, more or fewer items than CTAs, every RFI mode, dropped frames, repeated launches -- always the
-    bits of the monolithic kernel"""
+    odd item counts, more or fewer items than CTAs, every RFI mode, dropped frames, repeated launches"""
     gen = dict(drop_period=9, drop_len=1, drop_pol_skew=2, **RFI)
     for T, n in ((8, 1), (40, 3), (136, 2), (152, 1)):
         ins = [make_input(pkg, T, seed=90 + T, antenna=a, **gen) for a in range(n)]
         outs = []
-        for nt in (640, 0):
+        for nt in (640, 1, 0):
             with pkg.Pipeline(testing=True, ffts_per_seg=T, nbit=8, npol=2, rfi_mode=mode, n_antennas=n, k1_threads=nt) as p:
                 runs = []
                 for _ in range(3):
                     m, r = p.process_batch([i[0] for i in ins], [i[1] for i in ins])
                     runs.append((m, r, [p.get_mask(a) for a in range(n)] if mode else None))
                 outs.append(runs)
-        for a_run, b_run in zip(*outs):
+        # round 1's pipelined kernel (1) has the arithmetic of the monolithic one (640): identical bits; the product
+        # kernel (0) has another transform: identical masks, bytes equal up to samples on a rounding boundary
+        for a_run, b_run, c_run in zip(*outs):
             for a in range(n):
                 assert np.array_equal(a_run[0][a], b_run[0][a])
+                check_bytes(a_run[0][a], c_run[0][a], 8, "main T=%d antenna %d" % (T, a))
                 if mode == 2:
                     assert np.array_equal(a_run[1][a], b_run[1][a])
+                    check_bytes(a_run[1][a], c_run[1][a], 8, "raw T=%d antenna %d" % (T, a))
                 if mode:
                     assert np.array_equal(a_run[2][a], b_run[2][a])
+                    assert np.array_equal(a_run[2][a], c_run[2][a])
+        # and the product kernel is deterministic from launch to launch
+        with pkg.Pipeline(testing=True, ffts_per_seg=T, nbit=8, npol=2, rfi_mode=mode, n_antennas=n, k1_threads=0) as p:
+            for r_i, c_run in enumerate(outs[2]):
+                m, r = p.process_batch([i[0] for i in ins], [i[1] for i in ins])
+                for a in range(n):
+                    assert np.array_equal(m[a], c_run[0][a]), (T, r_i, a)
 
 
 def test_batched_launches_equal_per_segment(pkg):
@@ -273,8 +283,11 @@ def test_batched_launches_equal_per_segment(pkg):
 
 
 def test_k1_thread_variants_agree(pkg):
-    """the pipelined channeliser (0, the default) and the monolithic one at three CTA sizes give the same bits;
-    T = 1024 x 2 antennas makes every CTA of the pipelined kernel draw many items from the shared counter"""
+    """Testing build, A/B: the product channeliser (0: one polarisation per thread group, 6250-point real-input FFT)
+    against round 1's kernels with the two-for-one 12500-point FFT -- pipelined (1) and monolithic at three CTA
+    sizes.  Masks, weights, statistics and histogram do not depend on the FFT: identical.  The old variants agree
+    with each other bit for bit; the new transform rounds differently, so its bytes agree with theirs up to samples
+    on a rounding boundary.  T = 1024 makes every CTA of the pipelined kernels draw many items from the counter."""
     for T, n_seg in ((16, 1), (1024, 3)):
         _k1_variants(pkg, T, n_seg)
 
@@ -282,15 +295,19 @@ def test_k1_thread_variants_agree(pkg):
 def _k1_variants(pkg, T, n_seg):
     p0, p1 = make_input(pkg, T, seed=60, **RFI)
     outs = []
-    for nt in (0, 320, 512, 640) if T == 16 else (0, 640):
+    for nt in (0, 1, 320, 512, 640) if T == 16 else (0, 1, 640):
         with pkg.Pipeline(testing=True, ffts_per_seg=T, nbit=8, rfi_mode=2, k1_threads=nt, keep_stats=1, do_histo=1) as p:
             for _ in range(n_seg):          # several launches: the item counter is never reset
                 o = p.process_segment(p0, p1)
             outs.append(o + (p.get_mask(), p.get_stats()))
+    for o in outs[2:]:
+        assert np.array_equal(outs[1][0], o[0]) and np.array_equal(outs[1][1], o[1])
     for o in outs[1:]:
-        assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) and np.array_equal(outs[0][2], o[2])
+        assert np.array_equal(outs[0][2], o[2])
         for k in ("pow", "kur", "dag", "pow_fb", "kur_fb", "dag_fb", "weights", "histo"):
             assert np.array_equal(outs[0][3][k], o[3][k], equal_nan=True), k
+    check_bytes(outs[0][0], outs[1][0], 8, "main, new against old transform")
+    check_bytes(outs[0][1], outs[1][1], 8, "raw, new against old transform")
 
 
 def test_coadd_single_process(pkg, orc):

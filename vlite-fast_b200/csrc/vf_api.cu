@@ -91,6 +91,7 @@ struct vf_handle {
   int have_k2_last;
   float2 *bp_raw, *bp_kur;    /* [n_ant][4096] (pol0, pol1) */
   float2 *tw;                 /* tw1 | tw5 | tw500 */
+  float2 *tw6;                /* 6250-point FFT: tw1[250] | tw5[250] | tw250[240] | tws[6250] */
   float *wtab;                /* [26] */
   float *ave_main, *ave_raw;  /* [ave_nseg][n_ant][npol][T/8][4096] */
   float *rowok;               /* [ave_nseg][n_ant][T/8]: 1 = scrunched row of the main stream kept, 0 = zeroed (co-add count) */
@@ -263,7 +264,7 @@ int vf_destroy (vf_handle *h)
     for (int i = 0; i < 5; ++i) if (s->ev_t[i]) cudaEventDestroy (s->ev_t[i]);
     if (s->st) cudaStreamDestroy (s->st);
   }
-  cudaFree (h->bp_raw); cudaFree (h->bp_kur); cudaFree (h->tw); cudaFree (h->wtab);
+  cudaFree (h->bp_raw); cudaFree (h->bp_kur); cudaFree (h->tw); cudaFree (h->tw6); cudaFree (h->wtab);
   cudaFree (h->ave_main); cudaFree (h->ave_raw); cudaFree (h->rowok); free (h->ant_last); free (h->ant_seg);
   cudaFree (h->frb_delays); cudaFree (h->coadd_sum); cudaFree (h->coadd_out);
   if (h->ev_t0) cudaEventDestroy (h->ev_t0);
@@ -299,7 +300,7 @@ int vf_create (const vf_config *cfg, vf_handle **out)
   if (cfg->n_antennas < 1 || cfg->n_antennas > 4096) return VF_ERR_ARG;
   if (cfg->max_batch_segments < 0 || cfg->max_batch_segments > 64) return VF_ERR_ARG;
 #ifdef VF_TESTING
-  if (!(cfg->k1_threads == 0 || cfg->k1_threads == 320 || cfg->k1_threads == 512 || cfg->k1_threads == 640)) return VF_ERR_ARG;
+  if (!(cfg->k1_threads == 0 || cfg->k1_threads == 1 || cfg->k1_threads == 320 || cfg->k1_threads == 512 || cfg->k1_threads == 640)) return VF_ERR_ARG;
 #else
   if (cfg->k1_threads != 0) return VF_ERR_ARG;      /* the monolithic channeliser exists in testing builds only */
 #endif
@@ -365,6 +366,27 @@ int vf_create (const vf_config *cfg, vf_handle **out)
       }
     CK (cudaMalloc ((void **) &h->tw, 1500 * sizeof (float2)));
     CK (cudaMemcpy (h->tw, tw.data (), 1500 * sizeof (float2), cudaMemcpyHostToDevice));
+  }
+  /* the same for the 6250-point real-input FFT (vf_fft6250.cuh): w_6250^p, w_6250^(5p) (p < 250), w_250^(p' k)
+   * and the split twiddles w_12500^k (k < 6250) */
+  {
+    std::vector<float2> tw (VF_TW6_LEN);
+    for (int p = 0; p < 250; ++p) {
+      const double a1 = -2.0 * M_PI * p / 6250.0, a5 = -2.0 * M_PI * 5 * p / 6250.0;
+      tw[p] = make_float2 ((float) cos (a1), (float) sin (a1));
+      tw[250 + p] = make_float2 ((float) cos (a5), (float) sin (a5));
+    }
+    for (int k = 1; k < 25; ++k)
+      for (int pp = 0; pp < 10; ++pp) {
+        const double a = -2.0 * M_PI * (pp * k) / 250.0;
+        tw[500 + (k - 1) * 10 + pp] = make_float2 ((float) cos (a), (float) sin (a));
+      }
+    for (int k = 0; k < VF6_M; ++k) {
+      const double a = -2.0 * M_PI * k / 12500.0;
+      tw[740 + k] = make_float2 ((float) cos (a), (float) sin (a));
+    }
+    CK (cudaMalloc ((void **) &h->tw6, VF_TW6_LEN * sizeof (float2)));
+    CK (cudaMemcpy (h->tw6, tw.data (), VF_TW6_LEN * sizeof (float2), cudaMemcpyHostToDevice));
   }
   /* weight of an FFT block with k kept sub-blocks: k sequential float adds of
    * float(NKURTO)/NFFT (atomicAdd, src/pb_kernels.cu:292) */
@@ -514,6 +536,7 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int ant0, int n_ant, co
   }
   if (s->histo) k1.histo = s->histo + (size_t) ant0 * 512;
   k1.tb.tw1 = h->tw; k1.tb.tw5 = h->tw + 500; k1.tb.tw500 = h->tw + 1000;
+  k1.tb6.tw1 = h->tw6; k1.tb6.tw5 = h->tw6 + 250; k1.tb6.tw250 = h->tw6 + 500; k1.tb6.tws = h->tw6 + 740;
   memcpy (k1.dagc, h->dagc, sizeof (k1.dagc));
   memcpy (k1.dagc_fb, h->dagc_fb, sizeof (k1.dagc_fb));
   k1.dag_thresh = c.dag_thresh;
@@ -526,8 +549,8 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int ant0, int n_ant, co
   if (k1.histo) CK (cudaMemsetAsync (k1.histo, 0, (size_t) n_ant * 512 * sizeof (unsigned int), s->st));
   const int n_items = n_ant * n_seg * h->T;
   const int grid = n_items < h->nsm ? n_items : h->nsm;
-  const int threads = c.k1_threads;            /* 0: pipelined kernel; 320/512/640: monolithic kernel (testing builds, A/B) */
-  if (threads == 0) {
+  const int threads = c.k1_threads;            /* 0: the product kernel; testing builds, A/B: 1 = round 1's two-for-one pipelined kernel, 320/512/640 = monolithic kernel */
+  if (threads == 0 || threads == 1) {
     k1.work_counter = s->d_work;
     k1.work_base = s->work_base;
     s->work_base += (unsigned int) (n_items + 2 * grid);   /* what this launch draws (wraps with the counter) */

@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 #include "vf_fft12500.cuh"
+#include "vf_fft6250.cuh"
 
 #define VF_NCHAN_FFT   6251     /* NFFT/2+1, src/process_baseband.h:22 */
 #define VF_NSCRUNCH    8        /* :24 */
@@ -27,6 +28,7 @@
 #define VF_PBLK        VF_NCHANOUT
 #define VF_PIDX(T, c)  (((size_t) ((c) / VF_PBLK) * (size_t) (T)) * VF_PBLK + ((c) % VF_PBLK))   /* relative to time step t's base (t * VF_PBLK) */
 
+#define VF_TW6_LEN     (250 + 250 + 240 + VF6_M)   /* vf6_tables in one array: tw1 | tw5 | tw250 | tws */
 #define VF_WIN         12512    /* 16-byte aligned window that covers any 12500-sample block */
 
 /* Channeliser: one work item = one FFT time step of one antenna (both pols). */
@@ -40,7 +42,8 @@ struct vf_k1_params {
   float *pw, *kur, *dag;      /* optional [n_ant][2][T*25] */
   float *pw_fb, *kur_fb, *dag_fb;  /* optional [n_ant][2][T] */
   unsigned int *histo;        /* optional [n_ant][2][256] */
-  vf_fft_tables tb;
+  vf_fft_tables tb;           /* two-for-one 12500-point FFT (testing builds: the monolithic kernel) */
+  vf6_tables tb6;             /* 6250-point real-input FFT of the product kernel */
   double dagc[5], dagc_fb[5]; /* mu1, A, Z1, Z2, Z3 for N = 500 and N = 12500 */
   double dag_thresh;          /* DAG_THRESH, src/process_baseband.h:42 */
   const float *wtab;          /* [26] device: k-fold float sum of float(500)/12500 */
@@ -113,5 +116,4 @@ cudaError_t vf_launch_coadd_local (const vf_coadd_local_params &p, cudaStream_t 
 #ifdef VF_TESTING
 cudaError_t vf_launch_debug_div (const float *p, const float *b, float *q_packed, float *q_ref, size_t n, cudaStream_t s);
 #endif
-size_t vf_k1_smem_bytes (void);
 cudaError_t vf_k1_configure (void);
