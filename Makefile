@@ -13,15 +13,15 @@ LIB      := $(PKG)/libvlitefast.so
 TESTLIB  := $(PKG)/libvlitefast_testing.so
 GENLIB   := $(PKG)/libvlitegen.so
 
-all: $(LIB) $(TESTLIB) $(GENLIB) host oracle build/vf_fft_hosttest scripts/ubench/fp32_rate
+all: $(LIB) $(TESTLIB) $(GENLIB) host oracle build/vf_fft_hosttest build/vf_fft6250_hosttest scripts/ubench/fp32_rate
 
 build:
 	mkdir -p build
 
-build/vf_kernels.o: $(CSRC)/vf_kernels.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft12500.cuh $(CSRC)/vf_fft_consts.h $(CSRC)/vf_pass3_map.h | build
+build/vf_kernels.o: $(CSRC)/vf_kernels.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft12500.cuh $(CSRC)/vf_fft6250.cuh $(CSRC)/vf_fft_consts.h $(CSRC)/vf_pass3_map.h | build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-build/vf_api.o: $(CSRC)/vf_api.cu $(CSRC)/vf_kernels.h include/vlitefast.h | build
+build/vf_api.o: $(CSRC)/vf_api.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft6250.cuh include/vlitefast.h | build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 # -Bsymbolic: calls between the two objects bind inside the library, so that the product and the testing
@@ -31,10 +31,10 @@ $(LIB): build/vf_kernels.o build/vf_api.o
 
 # the same sources with -DVF_TESTING: adds the monolithic channeliser (vf_config.k1_threads) and
 # vf_debug_division (csrc/vf_testing.h).  Loaded by tests/ for A/B comparisons only.
-build/vf_kernels_t.o: $(CSRC)/vf_kernels.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft12500.cuh $(CSRC)/vf_fft_consts.h $(CSRC)/vf_pass3_map.h | build
+build/vf_kernels_t.o: $(CSRC)/vf_kernels.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft12500.cuh $(CSRC)/vf_fft6250.cuh $(CSRC)/vf_fft_consts.h $(CSRC)/vf_pass3_map.h | build
 	$(NVCC) $(NVFLAGS) -DVF_TESTING -c $< -o $@
 
-build/vf_api_t.o: $(CSRC)/vf_api.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_testing.h include/vlitefast.h | build
+build/vf_api_t.o: $(CSRC)/vf_api.cu $(CSRC)/vf_kernels.h $(CSRC)/vf_fft6250.cuh $(CSRC)/vf_testing.h include/vlitefast.h | build
 	$(NVCC) $(NVFLAGS) -DVF_TESTING -c $< -o $@
 
 $(TESTLIB): build/vf_kernels_t.o build/vf_api_t.o
@@ -49,6 +49,9 @@ scripts/ubench/fp32_rate: scripts/ubench/fp32_rate.cu
 	$(NVCC) -O3 $(GENCODE) -o $@ $<
 
 build/vf_fft_hosttest: $(CSRC)/vf_fft_hosttest.cu $(CSRC)/vf_fft12500.cuh | build
+	$(NVCC) -O2 -std=c++17 -I$(CSRC) -o $@ $<
+
+build/vf_fft6250_hosttest: $(CSRC)/vf_fft6250_hosttest.cu $(CSRC)/vf_fft6250.cuh $(CSRC)/vf_fft12500.cuh $(CSRC)/vf_fft_consts.h | build
 	$(NVCC) -O2 -std=c++17 -I$(CSRC) -o $@ $<
 
 host: $(LIB) $(GENLIB)

@@ -43,3 +43,30 @@ def test_two_for_one_fft(pkg, mask):
     for pol, x in enumerate((x0, x1)):
         Pr = np.abs(np.fft.rfft(x)[2155:2155 + 4096]) ** 2
         assert np.abs(P[:, pol] - Pr).max() / (Pr.mean() + 1e-30) < 1e-5
+
+
+EXE6 = os.path.join(ROOT, "build", "vf_fft6250_hosttest")
+
+
+@pytest.mark.skipif(not os.path.exists(EXE6), reason="build/vf_fft6250_hosttest not built")
+@pytest.mark.parametrize("fused", ["plain", "fused"])
+@pytest.mark.parametrize("mask", [0, 0x1, 0x1555555, 0x1FFFFFE])
+def test_real_input_fft(pkg, mask, fused):
+    """the product kernel's transform (csrc/vf_fft6250.cuh): one polarisation as a 6250-point complex FFT plus the
+    split pass, separately ("plain") and fused with pass 3 as the kernel runs it ("fused": every one of the 4096
+    channels must be written exactly by the 313 units)"""
+    b0, _ = make_input(pkg, 1, seed=21)
+    b0 = b0.copy(); b0[100:105] = 0
+    r = subprocess.run([EXE6, "%x" % mask, fused], input=b0.tobytes(), stdout=subprocess.PIPE, check=True)
+    out = np.frombuffer(r.stdout, np.float32)
+    P, Z = out[:4096], out[4096:].reshape(6250, 2)
+    Z = 2 * (Z[:, 0] + 1j * Z[:, 1])            # the transform runs at half scale (vf6_unpack_pair)
+    x = volts(b0)
+    for j in range(25):
+        if (mask >> j) & 1:
+            x[500 * j:500 * (j + 1)] = 0
+    Zr = np.fft.fft(x[0::2] + 1j * x[1::2])
+    assert np.abs(Z - Zr).max() / (np.sqrt((np.abs(Zr) ** 2).mean()) + 1e-30) < 3e-6
+    Pr = np.abs(np.fft.rfft(x)[2155:2155 + 4096]) ** 2
+    assert (P >= 0).all()
+    assert np.abs(P - Pr).max() / (Pr.mean() + 1e-30) < 1e-5

@@ -54,8 +54,11 @@ VF_HD void vf_dft10 (float2 (&v)[10])
   for (int d = 0; d < 5; ++d) vf_r2 (v[2 * d], v[2 * d + 1]);
 }
 
-/* two consecutive samples of one polarisation as (re, im): the bytes are sanitised (0 -> 128), 2^23 + u is built in the
- * mantissa and (2^23 + u) / 128 - 65537 is exact (src/pb_kernels.cu:23-33) */
+/* two consecutive samples of one polarisation as (re, im), at HALF the reference's scale: the bytes are sanitised
+ * (0 -> 128), 2^23 + u is built in the mantissa and (2^23 + u) / 256 - 32768.5 = (u - 128) / 256 is exact
+ * (src/pb_kernels.cu:23-33 has u / 128 - 1).  The transform is linear and scaling by a power of two is exact, so
+ * every Z is exactly half of what the full scale gives, and the split pass's X = (s - i t) / 2 needs no further factor:
+ * the powers are bit-identical to 0.25 |s - i t|^2 at full scale. */
 VF_HD float2 vf6_unpack_pair (const uint8_t *b)
 {
 #if defined(__CUDA_ARCH__)
@@ -64,7 +67,7 @@ VF_HD float2 vf6_unpack_pair (const uint8_t *b)
 #else
   const float2 v = make_float2 (8388608.0f + (float) b[0], 8388608.0f + (float) b[1]);
 #endif
-  return vf_fma2 (v, vf_bc (0.0078125f), vf_bc (-65537.0f));
+  return vf_fma2 (v, vf_bc (0.00390625f), vf_bc (-32768.5f));
 }
 
 /* pass 1: butterfly p in [0,250).  b points at (sanitised) sample 0 of this FFT block of one polarisation (2-byte
@@ -141,7 +144,7 @@ VF_HD float vf6_split_power (float2 a, float2 b, float2 w)
   const float2 d = vf_add2 (a, make_float2 (-b.x, b.y));
   const float2 t = vf_cmul (d, w);
   const float2 u = vf_add2 (s, make_float2 (t.y, -t.x));
-  return 0.25f * fmaf (u.x, u.x, u.y * u.y);
+  return fmaf (u.x, u.x, u.y * u.y);             /* Z at half scale (vf6_unpack_pair): u = X */
 }
 
 /* the same with the field amplitude scaled by amp (FRB injection, src/pb_kernels.cu:38-66) */
@@ -151,7 +154,7 @@ VF_HD float vf6_split_power_amp (float2 a, float2 b, float2 w, float amp)
   const float2 d = vf_add2 (a, make_float2 (-b.x, b.y));
   const float2 t = vf_cmul (d, w);
   const float2 u = vf_add2 (s, make_float2 (t.y, -t.x));
-  const float xr = 0.5f * u.x * amp, xi = 0.5f * u.y * amp;
+  const float xr = u.x * amp, xi = u.y * amp;
   return fmaf (xr, xr, xi * xi);
 }
 
@@ -169,6 +172,7 @@ VF_HD float vf6_detect (int c, const float2 *W, const float2 *tws)
  * outputs never go back to shared memory (saves the 6250 stores of pass 3, the 8192 loads of a separate split pass
  * and a barrier).  One pair (a = Z[k], b = Z[M - k], w = w_N^k) yields both mirror channels:
  *     s = a + conj b,  d = a - conj b,  t = w d,   |2 X[k]|^2 = |s - i t|^2,   |2 X[M - k]|^2 = |s + i t|^2
+ * (the transform runs at half scale, so the factor 2 is already in Z)
  * (w_N^(M - k) = -conj w_N^k turns the second into the conjugate of s + i t).
  * Kept channels are k = 2155..6250, channel index c = k - 2155: of a pair, X[k] is kept when k3 >= 4 or (k3 = 3 and
  * kb >= 280), X[M - k] (c = 4095 - k) when k3 <= 5 or (k3 = 6 and kb <= 345): compile-time except for two outputs.
@@ -185,8 +189,8 @@ VF_HD void vf6_mirror_powers (float2 a, float2 b, float2 w, float &pk, float &pm
   const float2 t = vf_cmul (d, w);
   const float2 um = vf_add2 (s, make_float2 (t.y, -t.x));      /* s - i t */
   const float2 up = vf_add2 (s, make_float2 (-t.y, t.x));      /* s + i t */
-  pk = 0.25f * fmaf (um.x, um.x, um.y * um.y);
-  pm = 0.25f * fmaf (up.x, up.x, up.y * up.y);
+  pk = fmaf (um.x, um.x, um.y * um.y);           /* Z at half scale (vf6_unpack_pair): um = X[k], up = conj X[M - k] */
+  pm = fmaf (up.x, up.x, up.y * up.y);
 }
 
 VF_HD void vf6_pass3_split (int u, const float2 *W, const float2 *tws, float *out)
@@ -200,15 +204,16 @@ VF_HD void vf6_pass3_split (int u, const float2 *W, const float2 *tws, float *ou
 #pragma unroll
   for (int j = 0; j < 10; ++j) { v1[j] = o1[j]; v2[j] = o2[j]; }
   if (u == 0) VF_ROT10 (v2);
+  float *const ok = out + 2 * (kb - 2155), *const om = out + 2 * (4095 - kb);      /* channel of X[kb], of X[M - kb] */
+  const float2 *const twk = tws + kb;
   vf_dft10 (v1);
   vf_dft10 (v2);
 #pragma unroll
   for (int k3 = 0; k3 < 10; ++k3) {
-    const int k = kb + 625 * k3;
     float pk, pm;
-    vf6_mirror_powers (v1[VF6_IDX (k3)], v2[VF6_IDX (9 - k3)], tws[k], pk, pm);
-    if (k3 >= 4 || (k3 == 3 && kb >= 280)) out[2 * (k - 2155)] = pk;
+    vf6_mirror_powers (v1[VF6_IDX (k3)], v2[VF6_IDX (9 - k3)], twk[625 * k3], pk, pm);
+    if (k3 >= 4 || (k3 == 3 && kb >= 280)) ok[2 * 625 * k3] = pk;
     /* unit 0: its mirror outputs are its own (written from the other side), except X[M] */
-    if ((k3 <= 5 || (k3 == 6 && kb <= 345)) && (u > 0 || k3 == 0)) out[2 * (4095 - k)] = pm;
+    if ((k3 <= 5 || (k3 == 6 && kb <= 345)) && (u > 0 || k3 == 0)) om[-2 * 625 * k3] = pm;
   }
 }
