@@ -64,9 +64,10 @@ typedef struct vf_config {
   int inject_frb;      /* 0      -i: allow vf_set_frb_injection                     */
   int gpu_id;          /* 0      -g                                                 */
   int n_antennas;      /* 1      antennas batched on this handle                    */
-  int k1_threads;      /* 0      must be 0 (the pipelined channeliser).  Testing builds of the library
-                                 (libvlitefast_testing.so) also take 320, 512 or 640: the monolithic
-                                 channeliser with that many threads, for A/B comparison       */
+  int k1_threads;      /* 0      must be 0 (the product channeliser).  Testing builds of the library
+                                 (libvlitefast_testing.so) also take round 1's kernels for A/B comparison:
+                                 1 = the pipelined channeliser with the two-for-one 12500-point FFT,
+                                 320, 512 or 640 = the monolithic channeliser with that many threads  */
   int power_segments;  /* 0      f32 tiles kept for this many consecutive segments (0 = 1): lets
                                  vf_coadd_batch reduce a whole second in one collective       */
   int max_batch_segments;/* 0    vf_process_device: consecutive segments per launch pair (0 = up to 16, 1 = one

@@ -1,7 +1,7 @@
 /*
  * TESTING BUILDS ONLY.  Entry points that exist in libvlitefast_testing.so (the product sources compiled
- * with -DVF_TESTING) and not in libvlitefast.so: the monolithic channeliser behind vf_config.k1_threads
- * (320 / 512 / 640) and the self-check below.  tests/ load this library for A/B comparisons only.
+ * with -DVF_TESTING) and not in libvlitefast.so: round 1's channelisers behind vf_config.k1_threads
+ * (1: pipelined, two-for-one FFT; 320 / 512 / 640: monolithic) and the self-checks below.  tests/ load this library for A/B comparisons only.
  */
 #ifndef VF_TESTING_H
 #define VF_TESTING_H
