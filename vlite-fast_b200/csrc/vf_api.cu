@@ -41,6 +41,8 @@ struct vf_slot {
   uint32_t *mask;             /* [n_ant][T] */
   uint8_t *d_out_main, *d_out_raw;   /* [n_ant][out_bytes] */
   cudaEvent_t ev_k2, ev_done;
+  cudaStream_t st_k2;         /* the normaliser's launches: highest priority (see vf_enqueue_segment) */
+  cudaEvent_t ev_k1done, ev_k2done;
   cudaEvent_t ev_t[5];        /* asynchronous submissions: start, before K1, after K1, after K2, end (vf_slot_elapsed_ms) */
   int t_valid;
   int pending;                /* vf_submit_*_async issued, vf_wait not yet called */
@@ -110,7 +112,7 @@ struct vf_handle {
   int coadd_next;
   float *coadd_sum;           /* [ave_nseg] summed tiles, then [ave_nseg][T/8] contributing-antenna counts: one reduce */
   uint8_t *coadd_out;
-  int debug_sync, serial;
+  int debug_sync, serial, k2_priority;
   long long *k2_trace;        /* testing builds: vf_debug_k2_trace */
   char err[512];
 };
@@ -205,6 +207,13 @@ static int vf_alloc_slot (vf_handle *h, vf_slot *s)
   const size_t na = (size_t) h->n_ant;
   const int mode = h->cfg.rfi_mode;
   CK (cudaStreamCreateWithFlags (&s->st, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    CK (cudaDeviceGetStreamPriorityRange (&lo, &hi));
+    CK (cudaStreamCreateWithPriority (&s->st_k2, cudaStreamNonBlocking, hi));
+    CK (cudaEventCreateWithFlags (&s->ev_k1done, cudaEventDisableTiming));
+    CK (cudaEventCreateWithFlags (&s->ev_k2done, cudaEventDisableTiming));
+  }
   CK (cudaMalloc ((void **) &s->d_in, na * 2 * h->nsamp));
   int rc = vf_alloc_tiles (h, s, 1);
   if (rc) return rc;
@@ -261,6 +270,9 @@ int vf_destroy (vf_handle *h)
     cudaFree (s->pw); cudaFree (s->pw_fb); cudaFree (s->histo);
     if (s->ev_k2) cudaEventDestroy (s->ev_k2);
     if (s->ev_done) cudaEventDestroy (s->ev_done);
+    if (s->ev_k1done) cudaEventDestroy (s->ev_k1done);
+    if (s->ev_k2done) cudaEventDestroy (s->ev_k2done);
+    if (s->st_k2) cudaStreamDestroy (s->st_k2);
     for (int i = 0; i < 5; ++i) if (s->ev_t[i]) cudaEventDestroy (s->ev_t[i]);
     if (s->st) cudaStreamDestroy (s->st);
   }
@@ -326,6 +338,7 @@ int vf_create (const vf_config *cfg, vf_handle **out)
   /* VF_SERIAL=1: no overlap between segments, so that the per-kernel event times of
    * vf_last_elapsed_ms are pure execution times (profiling aid) */
   { const char *e = getenv ("VF_SERIAL"); h->serial = e && *e == '1'; }
+  { const char *e = getenv ("VF_K2_PRIORITY"); h->k2_priority = !(e && *e == '0'); }     /* on unless VF_K2_PRIORITY=0 (A/B) */
 
   CK (cudaSetDevice (cfg->gpu_id));
   if (cfg->numa_pin) vf_bind_thread_to_gpu (cfg->gpu_id, NULL, 0);
@@ -563,15 +576,25 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int ant0, int n_ant, co
   if (timed >= 0) CK (cudaEventRecord (h->ev_kb[timed], s->st));
   if (timed == -2) CK (cudaEventRecord (s->ev_t[2], s->st));
 
+  /* The normaliser goes to a stream of its own with the highest priority: the channeliser of the NEXT submission
+   * (other slot) is usually queued already, and its persistent CTAs hold an SM each for the whole launch -- the block
+   * scheduler must hand the SMs that this submission's channeliser frees to this normaliser first (one wave of 128
+   * CTAs), and the next channeliser then starts on the 20 SMs that wave leaves idle.  Measured (round 2, bench, 1 antenna):
+   * 1118-1138 -> 1153 antenna-seconds/s. */
+  cudaStream_t k2st = h->k2_priority ? s->st_k2 : s->st;
+  if (h->k2_priority) {
+    CK (cudaEventRecord (s->ev_k1done, s->st));
+    CK (cudaStreamWaitEvent (k2st, s->ev_k1done, 0));
+  }
   /* the bandpass makes K2 launches sequential in segment order */
-  if (h->have_k2_last) CK (cudaStreamWaitEvent (s->st, h->ev_k2_last, 0));
+  if (h->have_k2_last) CK (cudaStreamWaitEvent (k2st, h->ev_k2_last, 0));
   /* segments enqueued so far for these antennas (they advance together): index into the ring of kept tiles */
   const long seg0 = h->ant_seg[ant0];
   /* this launch overwrites the tiles of segments [seg0 - ave_nseg, seg0 - ave_nseg + n_seg): wait for a co-add that still reads them */
   for (int b = 0; b < 2; ++b) {
     const long victim_lo = seg0 - h->ave_nseg, victim_hi = victim_lo + n_seg;    /* [lo, hi) */
     if (h->coadd_batch[b].pending && victim_lo < h->coadd_batch[b].hi && victim_hi > h->coadd_batch[b].lo) {
-      CK (cudaStreamWaitEvent (s->st, h->coadd_batch[b].ev, 0));
+      CK (cudaStreamWaitEvent (k2st, h->coadd_batch[b].ev, 0));
       h->coadd_batch[b].pending = 0;
     }
   }
@@ -611,11 +634,15 @@ static int vf_enqueue_segment (vf_handle *h, vf_slot *s, int ant0, int n_ant, co
     }
     h->last_n_ant = n_ant;
   }
-  CK (vf_launch_k2 (k2, s->st));
+  CK (vf_launch_k2 (k2, k2st));
+  CK (cudaEventRecord (h->ev_k2_last, k2st));
+  if (h->k2_priority) {
+    CK (cudaEventRecord (s->ev_k2done, k2st));
+    CK (cudaStreamWaitEvent (s->st, s->ev_k2done, 0));      /* copies out, and the slot's next channeliser, follow on the slot's stream */
+  }
   if (h->debug_sync) CK (cudaStreamSynchronize (s->st));
   if (timed >= 0) CK (cudaEventRecord (h->ev_kc[timed], s->st));
   if (timed == -2) CK (cudaEventRecord (s->ev_t[3], s->st));
-  CK (cudaEventRecord (h->ev_k2_last, s->st));
   h->have_k2_last = 1;
   return VF_OK;
 }
