@@ -658,10 +658,10 @@ static int vf_timing_begin (vf_handle *h, int n_timed)
     }
   h->n_timed = n_timed;
   h->timed_valid = 0;
-  /* fork: both slot streams start after ev_t0 on the control stream */
-  CK (cudaEventRecord (h->ev_t0, h->ctl));
-  CK (cudaStreamWaitEvent (h->slot[0].st, h->ev_t0, 0));
-  CK (cudaStreamWaitEvent (h->slot[1].st, h->ev_t0, 0));
+  /* the call's clock starts where its first launch does: on the stream of the slot it uses first.  (No fork from the
+   * control stream: that made every call wait for the whole of the previous one -- the control stream had joined both
+   * slots -- so the channeliser of a call never ran beside the normaliser of the one before.) */
+  CK (cudaEventRecord (h->ev_t0, h->slot[h->next_slot].st));
   return VF_OK;
 }
 
