@@ -226,7 +226,7 @@ def main():
     # pinned buffers are allocated from here on: sit on the GPU's NUMA node first
     cpulist = pkg.bind_thread_to_gpu(local)
     p = pkg.Pipeline(ffts_per_seg=T, nbit=args.nbit, npol=args.npol, rfi_mode=args.rfi_mode, gpu_id=local,
-                     n_antennas=n_ant, keep_power=1, max_batch_segments=args.max_batch, power_segments=2 * SEG_PER_SEC)
+                     n_antennas=n_ant, keep_power=1, max_batch_segments=args.max_batch, power_segments=4 * SEG_PER_SEC)
     out_bytes = p.out_bytes
     nstream = 2 if args.rfi_mode == 2 else 1
     coadd_bytes = args.npol * (T // 8) * 4096 * args.nbit // 8       # per segment
