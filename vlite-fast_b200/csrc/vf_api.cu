@@ -82,9 +82,7 @@ struct vf_handle {
   size_t tile_elems;          /* T*4096 per antenna */
   cudaStream_t ctl;
   cudaStream_t coadd_st;      /* co-add runs beside the next segments, not in front of them */
-  cudaStream_t coadd_hi;      /* highest priority: the local sum and the reduce of a multi-rank co-add */
-  cudaEvent_t ev_reduced, ev_sumfree;   /* reduce done; the root's digitiser and copies have read the sum buffer */
-  int have_sumfree;
+  cudaStream_t coadd_hi;      /* highest priority: a multi-rank co-add (vf_coadd_batch) */
   vf_slot slot[2];
   int batch_cap;              /* consecutive segments the tile / weight / mask buffers of a slot hold */
   int last_n_ant;             /* antennas of the last launch (the co-add sums that many tiles) */
@@ -296,8 +294,6 @@ int vf_destroy (vf_handle *h)
   if (h->ctl) cudaStreamDestroy (h->ctl);
   if (h->coadd_st) cudaStreamDestroy (h->coadd_st);
   if (h->coadd_hi) cudaStreamDestroy (h->coadd_hi);
-  if (h->ev_reduced) cudaEventDestroy (h->ev_reduced);
-  if (h->ev_sumfree) cudaEventDestroy (h->ev_sumfree);
   free (h);
   return VF_OK;
 }
@@ -362,8 +358,6 @@ int vf_create (const vf_config *cfg, vf_handle **out)
     CK (cudaDeviceGetStreamPriorityRange (&lo, &hi));
     { const char *e = getenv ("VF_COADD_PRIORITY"); if (e && *e == '0') hi = lo; }      /* A/B */
     CK (cudaStreamCreateWithPriority (&h->coadd_hi, cudaStreamNonBlocking, hi));
-    CK (cudaEventCreateWithFlags (&h->ev_reduced, cudaEventDisableTiming));
-    CK (cudaEventCreateWithFlags (&h->ev_sumfree, cudaEventDisableTiming));
   }
   for (int i = 0; i < 2; ++i) {
     int rc = vf_alloc_slot (h, &h->slot[i]);
@@ -1388,16 +1382,14 @@ int vf_coadd_batch (vf_handle *h, int root, int total_antennas, int n_seg, uint8
   const size_t n = (size_t) h->cfg.npol * h->ntime * VF_NCHANOUT;        /* one tile */
   const size_t out1 = n * h->cfg.nbit / 8;
   float *cnt = h->coadd_sum + (size_t) n_seg * n;                        /* [n_seg][T/8] right behind the sums */
-  cudaStream_t st = h->coadd_st;
-  /* Multi-rank: the local sum and the reduce go to the highest-priority stream -- the reduce couples the ranks, and
-   * behind the queued CTAs of the next persistent channeliser it would start a whole launch later (2 GPUs, round 2:
-   * 2171 -> 2309 antenna-seconds/s); the root's divide-and-digitise and the copies out stay at normal priority, in the
-   * shadow of the next normaliser.  Single rank: nothing to couple, everything at normal priority (at highest priority
-   * the co-add's kernels sit in front of the channeliser: 1223 -> 1182). */
-  cudaStream_t st1 = h->nranks > 1 ? h->coadd_hi : st;
-  /* after every K2 that wrote the tiles, and after the previous batch's digitiser has read the sum buffer */
-  if (h->have_k2_last) CK (cudaStreamWaitEvent (st1, h->ev_k2_last, 0));
-  if (st1 != st && h->have_sumfree) CK (cudaStreamWaitEvent (st1, h->ev_sumfree, 0));
+  /* Multi-rank: the co-add goes to the highest-priority stream -- the reduce couples the ranks, and behind the queued
+   * CTAs of the next persistent channeliser it would start a whole launch later (2 GPUs, round 2: 2171-2177 ->
+   * 2309-2333 antenna-seconds/s; with only the local sum and the reduce there and the root's digitiser at normal
+   * priority: 2298).  Single rank: nothing to couple, and at highest priority the co-add's kernels sit in front of the
+   * channeliser instead of in the shadow of the next normaliser (1224 -> 1182): normal priority. */
+  cudaStream_t st = h->nranks > 1 ? h->coadd_hi : h->coadd_st;
+  /* after every K2 that wrote the tiles */
+  if (h->have_k2_last) CK (cudaStreamWaitEvent (st, h->ev_k2_last, 0));
   /* local sum and count over this handle's antennas, the segments of the batch in time order, one launch */
   {
     vf_coadd_local_params lp;
@@ -1405,16 +1397,12 @@ int vf_coadd_batch (vf_handle *h, int root, int total_antennas, int n_seg, uint8
     lp.seg0 = seg_end - n_seg; lp.nring = h->ave_nseg; lp.n_ant_total = h->n_ant;
     lp.n_ant = na; lp.ntime = h->ntime; lp.npol = h->cfg.npol; lp.n_seg = n_seg;
     lp.sum = h->coadd_sum; lp.cnt = cnt;
-    CK (vf_launch_coadd_local (lp, st1));
+    CK (vf_launch_coadd_local (lp, st));
   }
   if (h->nranks > 1) {
     /* ncclFloat32 = 7, ncclSum = 0 (nccl.h); one collective for the whole batch, sums and counts */
-    int e = g_nccl.Reduce (h->coadd_sum, h->coadd_sum, (n + h->ntime) * n_seg, 7, 0, root, h->comm, st1);
+    int e = g_nccl.Reduce (h->coadd_sum, h->coadd_sum, (n + h->ntime) * n_seg, 7, 0, root, h->comm, st);
     if (e != 0) return vf_fail (h, VF_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString (e) : "?");
-  }
-  if (st1 != st) {
-    CK (cudaEventRecord (h->ev_reduced, st1));
-    CK (cudaStreamWaitEvent (st, h->ev_reduced, 0));
   }
   if (h->rank == root) {
     vf_coadd_params cp;
@@ -1423,10 +1411,6 @@ int vf_coadd_batch (vf_handle *h, int root, int total_antennas, int n_seg, uint8
     CK (vf_launch_coadd (cp, st));
     if (fb_coadd) CK (cudaMemcpyAsync (fb_coadd, h->coadd_out, out1 * n_seg, cudaMemcpyDeviceToHost, st));
     if (sum_f32) CK (cudaMemcpyAsync (sum_f32, h->coadd_sum, n * n_seg * sizeof (float), cudaMemcpyDeviceToHost, st));
-  }
-  if (st1 != st) {
-    CK (cudaEventRecord (h->ev_sumfree, st));
-    h->have_sumfree = 1;
   }
   /* later segments overwrite the tile ring: those that hit this batch's tiles wait for it */
   {
