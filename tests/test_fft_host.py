@@ -70,3 +70,13 @@ def test_real_input_fft(pkg, mask, fused):
     Pr = np.abs(np.fft.rfft(x)[2155:2155 + 4096]) ** 2
     assert (P >= 0).all()
     assert np.abs(P - Pr).max() / (Pr.mean() + 1e-30) < 1e-5
+
+
+@pytest.mark.skipif(not os.path.exists(EXE6), reason="build/vf_fft6250_hosttest not built")
+def test_fused_pass_writes_every_channel_exactly_once(pkg):
+    """the 313 units of the fused pass 3 partition the 4096 kept channels of a polarisation: every channel is written
+    by exactly one unit (two would race in the kernel), and nothing lands in the other polarisation's slots"""
+    b0, _ = make_input(pkg, 1, seed=22)
+    r = subprocess.run([EXE6, "0", "count"], input=b0.tobytes(), stdout=subprocess.PIPE, check=True)
+    cnt = np.frombuffer(r.stdout, np.int32)
+    assert cnt.shape == (4096,) and (cnt == 1).all(), np.unique(cnt)

@@ -45,6 +45,18 @@ int main (int argc, char **argv)
   const bool fused = argc > 2 && !strcmp (argv[2], "fused");
   std::vector<float> P (4096), P2 (2 * 4096, -1.f);
   if (fused) for (int u = 0; u < VF6_NU; ++u) vf6_pass3_split (u, W.data (), tws.data (), P2.data ());
+  /* argv[2] = "count": how many units write each channel (must be exactly one: two units writing the same channel
+   * would race in the kernel).  Each unit runs into a buffer of its own, pre-filled with -1. */
+  if (argc > 2 && !strcmp (argv[2], "count")) {
+    std::vector<int> cnt (4096, 0);
+    for (int u = 0; u < VF6_NU; ++u) {
+      std::vector<float> Q (2 * 4096, -1.f);
+      vf6_pass3_split (u, W.data (), tws.data (), Q.data ());
+      for (int c = 0; c < 4096; ++c) { if (Q[2 * c] >= 0.f) cnt[c]++; if (Q[2 * c + 1] >= 0.f) cnt[c] += 1000; }   /* odd slots: the other polarisation's */
+    }
+    fwrite (cnt.data (), sizeof (int), 4096, stdout);
+    return 0;
+  }
   for (int m = 0; m < VF6_NC; ++m) vf6_pass3 (m, W.data ());
   std::vector<float2> Z (6250);
   for (int c = 0; c < 4096; ++c) P[c] = fused ? P2[2 * c] : vf6_detect (c, W.data (), tws.data ());
